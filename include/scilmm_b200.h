@@ -1,0 +1,129 @@
+/*
+ * scilmm_b200 — C-ABI of the B200-native estimation engine behind SciLMM's SparseCholesky path.
+ *
+ * The reference is pure Python (scilmm/SparseCholesky.py); its "FFI" for this path is the set of calls it
+ * makes into sksparse.cholmod / scipy.sparse.  Each entry point below names the reference call site(s) it
+ * replaces.  All pointers are plain host or device pointers (no torch / numpy types); `d_` = device memory
+ * on the current CUDA device, `h_` = host memory.  All matrices are FP64 with int32 indices (the reference
+ * hard-codes use_long=False, SparseCholesky.py:17).  Dense multi-column blocks are C-ordered n x k
+ * (the layout numpy hands the reference), i.e. the k values of one individual are contiguous.
+ *
+ * Every function returns SLMM_OK (0) or an error code; slmm_last_error() gives the message.
+ * Handles are not thread-safe; all work is issued on the legacy default stream (ordered with torch's
+ * default stream).  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef SCILMM_B200_H
+#define SCILMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLMM_OK 0
+#define SLMM_ERR_INVALID 1
+#define SLMM_ERR_CUDA 2
+#define SLMM_ERR_NOT_POSDEF 3   /* CholmodNotPositiveDefiniteError analogue */
+#define SLMM_ERR_INTERNAL 4
+
+#define SLMM_ORDER_NATURAL 0
+#define SLMM_ORDER_GIVEN 1
+#define SLMM_ORDER_METIS 2      /* nested dissection, the reference default ordering_method='nesdis' (:17) */
+#define SLMM_ORDER_MINDEG 3
+
+typedef struct slmm_chol slmm_chol_t;       /* symbolic analysis + numeric supernodal factor */
+typedef struct slmm_matset slmm_matset_t;   /* K device-resident CSR relationship matrices */
+
+const char* slmm_last_error(void);
+int slmm_version(void);
+int slmm_device_count(int* out);
+
+/* ------------------------------------------------------------------ sparse relationship matrices ------ */
+/* K CSR matrices (n x n, sorted indices, both triangles), the `mats` / `mat_list` arguments of
+ * HE / REML / compute_gradients (SparseCholesky.py:62,177,192). */
+int slmm_matset_create(int32_t n, int32_t K, slmm_matset_t** out);
+int slmm_matset_destroy(slmm_matset_t* ms);
+/* copy matrix k from host CSR arrays; identical patterns are detected and shared on the device */
+int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* h_indptr, const int32_t* h_indices,
+                       const double* h_data);
+/* borrow device-resident CSR arrays for matrix k (same_as >= 0: pattern identical to matrix same_as) */
+int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indptr, const int32_t* d_indices,
+                            const double* d_data, int64_t nnz, int32_t same_as);
+int slmm_matset_nnz(const slmm_matset_t* ms, int32_t k, int64_t* out);
+int slmm_matset_values(const slmm_matset_t* ms, int32_t k, const double** d_data_out);
+
+/* Haseman-Elston moments over rows [row_begin,row_end) (row-block shard), replaces the scipy calls
+ *   y.dot(A_i.dot(y)) - A_i.diagonal().dot(y**2)                       SparseCholesky.py:223
+ *   (A_i.multiply(A_j)).sum() - A_i.diagonal().dot(A_j.diagonal())     SparseCholesky.py:229 (and :237,:241)
+ * d_out (device, 2K + 2K*K doubles): [q_off(K) | q_diag(K) | S_off(K*K) | S_diag(K*K)], where *_off sums
+ * entries with row != col and *_diag the diagonal ones.  Partial sums of different shards simply add. */
+int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t row_begin, int32_t row_end, double* d_out);
+/* whole fit from host buffers (H2D of y, kernels, D2H of the moments): the e2e path */
+int slmm_he_moments_host(slmm_matset_t* ms, const double* h_y, double* h_out);
+
+/* out = A_k X for a C-ordered n x ncols block (mats[i].dot(X), SparseCholesky.py:65,66,70,157,161) */
+int slmm_spmm(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, double* d_out);
+/* d_out[c] = sum_i X[i,c] (A_k X)[i,c] over rows [row_begin,row_end) without materialising A_k X:
+ * np.sum(mats[i].dot(sim_vec) * sim_vec, axis=0) and invV_y.dot(mats[i].dot(invV_y)) (SparseCholesky.py:65-66) */
+int slmm_spmm_coldot(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, int32_t row_begin,
+                     int32_t row_end, double* d_out);
+
+/* ------------------------------------------------------------------ sparse Cholesky ------------------- */
+/* Symbolic analysis of a symmetric pattern given as CSR/CSC with both triangles (host arrays).  Replaces the
+ * analyze half of sksparse.cholmod.cholesky (SparseCholesky.py:22-26); done once per pattern.
+ * h_user_perm (perm[new] = old) is read when ordering == SLMM_ORDER_GIVEN. */
+int slmm_chol_analyze(int32_t n, const int32_t* h_indptr, const int32_t* h_indices, int32_t ordering,
+                      const int32_t* h_user_perm, slmm_chol_t** out);
+int slmm_chol_destroy(slmm_chol_t* h);
+/* i[0]=n i[1]=nsuper i[2]=nlevels i[3]=nnz(L) (sum of column counts) i[4]=stored panel doubles
+ * i[5]=exported nnz of L() i[6]=max front rows i[7]=max supernode cols i[8]=components
+ * i[9]=kernel launches per factorization i[10]=device bytes held
+ * d[0]=flops (sum colcount^2) d[1]=ordering seconds d[2]=symbolic seconds d[3]=dense flops actually issued */
+int slmm_chol_stats(const slmm_chol_t* h, int64_t* i_out, double* d_out);
+/* factor.P() (SparseCholesky.py:93): A[P][:,P] = L L' */
+int slmm_chol_perm(const slmm_chol_t* h, int32_t* h_perm);
+
+/* Register the pattern of one input matrix (any CSR/CSC subset of the analysed pattern, host arrays) and get a
+ * scatter map id; values with that pattern can then be streamed into the factor storage. */
+int slmm_chol_register_pattern(slmm_chol_t* h, const int32_t* h_indptr, const int32_t* h_indices, int32_t* map_id);
+/* V assembly (matrices_weighted_sum, SparseCholesky.py:55-59), fused with the scatter into the permuted
+ * supernodal panels:  panels = 0 ; panels += sigma * values  for each call, in call order (rounded multiply then
+ * rounded add, the order scipy uses).  first != 0 clears the panels before adding. */
+int slmm_chol_add_values(slmm_chol_t* h, int32_t map_id, const double* d_values, double sigma, int32_t first);
+/* numeric supernodal LL' (the factorize half of sksparse.cholmod.cholesky).  On a non-positive pivot returns
+ * SLMM_ERR_NOT_POSDEF and *fail_col = failing column in permuted order. */
+int slmm_chol_factorize(slmm_chol_t* h, int32_t* fail_col);
+/* factor.logdet() (SparseCholesky.py:40) */
+int slmm_chol_logdet(slmm_chol_t* h, double* h_out);
+/* factor(b) = solve_A (SparseCholesky.py:30,32,52,100,149,153): in-place on a C-ordered n x nrhs device block,
+ * original ordering.  mode 0: V^-1 b;  1: forward half only (L^-1 P b, permuted order);  2: backward half only. */
+int slmm_chol_solve(slmm_chol_t* h, double* d_B, int32_t nrhs, int32_t mode);
+/* (factor.L().dot(Z))[argsort(P)]  (SparseCholesky.py:50-51): d_out in original ordering, C-ordered n x nrhs */
+int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrhs);
+/* factor.L() as host CSC (colptr int64[n+1], rowidx int32[nnz], values double[nnz]; nnz = stats i[5]) */
+int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, double* h_values);
+
+/* Host-only view of the symbolic analysis (no CUDA device needed): used by the host-logic tests and to size a
+ * problem before touching the GPU.  i_out as slmm_chol_stats i[0..8] plus i[9]=total rows entries; the array
+ * getters may be NULL. */
+typedef struct slmm_symbolic slmm_symbolic_t;
+int slmm_symbolic_create(int32_t n, const int32_t* h_indptr, const int32_t* h_indices, int32_t ordering,
+                         const int32_t* h_user_perm, slmm_symbolic_t** out);
+int slmm_symbolic_destroy(slmm_symbolic_t* s);
+int slmm_symbolic_stats(const slmm_symbolic_t* s, int64_t* i_out, double* d_out);
+int slmm_symbolic_arrays(const slmm_symbolic_t* s, int32_t* perm, int32_t* parent, int32_t* colcount,
+                         int32_t* sn_first, int32_t* sn_nrow, int32_t* sn_parent, int64_t* sn_rowptr,
+                         int64_t* sn_lptr, int32_t* rows, int32_t* rel, int32_t* level_ptr, int32_t* level_sn);
+/* scatter map of a registered pattern into the panel storage (what slmm_chol_register_pattern uploads) */
+int slmm_symbolic_entry_map(const slmm_symbolic_t* s, const int32_t* h_indptr, const int32_t* h_indices,
+                            int64_t* h_target);
+
+/* FP64 DMMA self-test / microbenchmark of the tile GEMM (C = A B^T, column-major); returns elapsed ms */
+int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,
+                       int32_t lower, int32_t reps, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

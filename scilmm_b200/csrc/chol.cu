@@ -1,0 +1,817 @@
+// Numeric supernodal LL' factorization, logdet, multi-RHS solves and L*Z on the device.
+// Host code here only builds launch schedules (once per pattern / per RHS width) and walks them.
+//
+// Data layout in HBM
+//   panels   : for supernode s the ms x ns column-major trapezoid (ld = ms) at sn_lptr[s]; strict upper part of
+//              the diagonal block stays zero.
+//   inverses : one 64 x 64 column-major slot per diagonal block (TRSM and the triangular solves become GEMMs).
+//   arena[2] : update (Schur complement) matrices rs x rs, ping-pong by depth parity, so a child's update lives
+//              exactly until its parent's level has pulled it (parent-pull extend-add: atomics-free, fixed order).
+//   RHS      : permuted n x nrhs row-major block + per-level contribution blocks rs x nrhs (same ping-pong).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "dense_tiles.cuh"
+#include "symbolic.h"
+
+namespace slmm {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+constexpr int NBO = 256;   // outer block: columns updated together with K = NBO
+
+struct PullItem { int32_t p, c0, c1; };
+
+struct DevSym {
+  const int32_t *sn_first, *sn_nrow, *rows, *rel, *child_ptr, *child_idx;
+  const int64_t *sn_rowptr, *sn_lptr, *sn_uptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+__global__ void scatter_axpy_kernel(const int64_t* __restrict__ map, const double* __restrict__ vals, double sigma,
+                                    double* __restrict__ Lx, int64_t nnz) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < nnz; e += stride) {
+    const int64_t tgt = map[e];
+    if (tgt >= 0) Lx[tgt] = __dadd_rn(Lx[tgt], __dmul_rn(sigma, vals[e]));   // no FMA: scipy rounds twice
+  }
+}
+
+__device__ __forceinline__ int lower_bound_dev(const int32_t* a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// Parent-pull extend-add of the children's update matrices.  One warp owns target columns [c0,c1) of one
+// parent front and walks the children in fixed order, so no two warps ever write the same entry.
+__global__ void extend_add_kernel(const PullItem* __restrict__ items, int nitems, DevSym S, double* __restrict__ Lx,
+                                  const double* __restrict__ arena_child, double* __restrict__ arena_parent) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nitems) return;
+  const PullItem it = items[w];
+  const int p = it.p;
+  const int nsp = S.sn_first[p + 1] - S.sn_first[p], msp = S.sn_nrow[p], rsp = msp - nsp;
+  double* panel = Lx + S.sn_lptr[p];
+  double* Up = arena_parent + S.sn_uptr[p];
+  for (int q = S.child_ptr[p]; q < S.child_ptr[p + 1]; q++) {
+    const int c = S.child_idx[q];
+    const int nsc = S.sn_first[c + 1] - S.sn_first[c], rsc = S.sn_nrow[c] - nsc;
+    if (rsc == 0) continue;
+    const int32_t* relc = S.rel + S.sn_rowptr[c] + nsc;
+    const double* Uc = arena_child + S.sn_uptr[c];
+    const int ta = lower_bound_dev(relc, rsc, it.c0), tb = lower_bound_dev(relc, rsc, it.c1);
+    for (int tt = ta; tt < tb; tt++) {
+      const int pc = relc[tt];
+      const double* src = Uc + (int64_t)tt * rsc;
+      if (pc < nsp) {
+        double* dst = panel + (int64_t)pc * msp;
+        for (int u = tt + lane; u < rsc; u += 32) dst[relc[u]] += src[u];
+      } else {
+        double* dst = Up + (int64_t)(pc - nsp) * rsp - nsp;
+        for (int u = tt + lane; u < rsc; u += 32) dst[relc[u]] += src[u];
+      }
+    }
+  }
+}
+
+// Same pull for RHS blocks: target rows [c0,c1) of the parent front; rows < ns land in the permuted solution
+// block, the others in the parent's contribution block.  `sign` lets L*Z reuse it.
+__global__ void vec_pull_kernel(const PullItem* __restrict__ items, int nitems, DevSym S, double* __restrict__ X,
+                                const double* __restrict__ arena_child, double* __restrict__ arena_parent,
+                                const int64_t* __restrict__ vptr, int nrhs) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nitems) return;
+  const PullItem it = items[w];
+  const int p = it.p;
+  const int fp = S.sn_first[p], nsp = S.sn_first[p + 1] - fp;
+  double* Vp = arena_parent + vptr[p];
+  for (int q = S.child_ptr[p]; q < S.child_ptr[p + 1]; q++) {
+    const int c = S.child_idx[q];
+    const int nsc = S.sn_first[c + 1] - S.sn_first[c], rsc = S.sn_nrow[c] - nsc;
+    if (rsc == 0) continue;
+    const int32_t* relc = S.rel + S.sn_rowptr[c] + nsc;
+    const double* Vc = arena_child + vptr[c];
+    const int ta = lower_bound_dev(relc, rsc, it.c0), tb = lower_bound_dev(relc, rsc, it.c1);
+    for (int tt = ta; tt < tb; tt++) {
+      const int pr = relc[tt];
+      const double* src = Vc + (int64_t)tt * nrhs;
+      double* dst = pr < nsp ? X + (int64_t)(fp + pr) * nrhs : Vp + (int64_t)(pr - nsp) * nrhs;
+      for (int j = lane; j < nrhs; j += 32) dst[j] += src[j];
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                   const int32_t* __restrict__ perm, int n, int nrhs, int scatter) {
+  // gather: dst[i,:] = src[perm[i],:]   scatter: dst[perm[i],:] = src[i,:]
+  const int64_t total = (int64_t)n * nrhs;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(q / nrhs), j = (int)(q % nrhs);
+    const int64_t o = (int64_t)perm[i] * nrhs + j;
+    if (scatter) dst[o] = src[q]; else dst[q] = src[o];
+  }
+}
+
+__global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __restrict__ col2sn,
+                              const int32_t* __restrict__ sn_first, const int32_t* __restrict__ sn_nrow,
+                              const int64_t* __restrict__ sn_lptr, int n, double* __restrict__ partial) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int s = col2sn[j], c = j - sn_first[s];
+    acc += log(Lx[sn_lptr[s] + (int64_t)c * sn_nrow[s] + c]);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct Launch {
+  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, MEMSET } kind;
+  int64_t off;      // offset into the matching op array
+  int32_t count;    // ops / items
+  int32_t grid;     // CTAs
+  int32_t child_parity;
+};
+
+constexpr int BIG_SMEM = 2 * 16 * (128 + 4) * 2 * 8;
+constexpr int SMALL_SMEM = 2 * 16 * (64 + 4) * 2 * 8;
+
+struct Schedule {
+  std::vector<Launch> launches;
+  std::vector<GemmOp> gemm;
+  std::vector<PotrfOp> potrf;
+  std::vector<PullItem> pull;
+  GemmOp* d_gemm = nullptr;
+  PotrfOp* d_potrf = nullptr;
+  PullItem* d_pull = nullptr;
+  double flops = 0;
+  void upload() {
+    d_gemm = dev_upload(gemm.data(), gemm.size());
+    d_potrf = dev_upload(potrf.data(), potrf.size());
+    d_pull = dev_upload(pull.data(), pull.size());
+  }
+  void release() {
+    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull);
+    d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr;
+  }
+  size_t device_bytes() const {
+    return gemm.size() * sizeof(GemmOp) + potrf.size() * sizeof(PotrfOp) + pull.size() * sizeof(PullItem);
+  }
+};
+
+// collects the GEMM ops of one phase and splits them into the two tile configurations
+struct PhaseBuilder {
+  std::vector<GemmOp> big, small;
+  std::vector<PotrfOp> potrf;
+  void add(GemmOp op) {
+    if (op.M <= 0 || op.N <= 0 || op.K <= 0) return;
+    op.a_kidx = op.a_kidx;
+    if (op.M > 64 && op.N > 64) big.push_back(op); else small.push_back(op);
+  }
+  void flush(Schedule& sch) {
+    if (!potrf.empty()) {
+      sch.launches.push_back({Launch::POTRF, (int64_t)sch.potrf.size(), (int32_t)potrf.size(), (int32_t)potrf.size(), 0});
+      sch.potrf.insert(sch.potrf.end(), potrf.begin(), potrf.end());
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      std::vector<GemmOp>& v = pass == 0 ? big : small;
+      if (v.empty()) continue;
+      const int T = pass == 0 ? 128 : 64;
+      int64_t tiles = 0;
+      for (GemmOp& op : v) {
+        op.tiles_m = (op.M + T - 1) / T;
+        op.tiles_n = (op.N + T - 1) / T;
+        op.tile_start = (int32_t)tiles;
+        tiles += (int64_t)op.tiles_m * op.tiles_n;
+        double f = 2.0 * op.M * op.N * op.K;
+        sch.flops += (op.flags & GF_LOWER) ? 0.5 * f : f;
+      }
+      if (tiles > 2000000000LL) throw std::runtime_error("too many tiles in one phase");
+      sch.launches.push_back({pass == 0 ? Launch::GEMM_BIG : Launch::GEMM_SMALL, (int64_t)sch.gemm.size(),
+                              (int32_t)v.size(), (int32_t)tiles, 0});
+      sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
+    }
+    big.clear(); small.clear(); potrf.clear();
+  }
+};
+
+static GemmOp make_op(double* C, int64_t c_si, int64_t c_sj, const double* A, int64_t a_si, int64_t a_sk,
+                      const double* B, int64_t b_sj, int64_t b_sk, int M, int N, int K, int flags,
+                      const int32_t* kidx = nullptr) {
+  GemmOp op;
+  memset(&op, 0, sizeof(op));
+  op.C = C; op.A = A; op.B = B; op.a_kidx = kidx;
+  op.c_si = c_si; op.c_sj = c_sj; op.a_si = a_si; op.a_sk = a_sk; op.b_sj = b_sj; op.b_sk = b_sk;
+  op.M = M; op.N = N; op.K = K; op.flags = flags;
+  return op;
+}
+
+struct SolvePlan {
+  int nrhs = 0;
+  double *X = nullptr, *X2 = nullptr;
+  double* arena[2] = {nullptr, nullptr};
+  int64_t* d_vptr = nullptr;
+  Schedule fwd, bwd, lmul;
+  size_t bytes = 0;
+  void release() {
+    dev_free(X); dev_free(X2); dev_free(arena[0]); dev_free(arena[1]); dev_free(d_vptr);
+    fwd.release(); bwd.release(); lmul.release();
+  }
+};
+
+struct EntryMap { int64_t* d_map = nullptr; int64_t nnz = 0; };
+
+}  // namespace slmm
+
+using namespace slmm;
+
+struct slmm_chol {
+  Symbolic S;
+  // device copies of the symbolic structure
+  int32_t *d_sn_first = nullptr, *d_sn_nrow = nullptr, *d_rows = nullptr, *d_rel = nullptr, *d_child_ptr = nullptr,
+          *d_child_idx = nullptr, *d_col2sn = nullptr, *d_perm = nullptr;
+  int64_t *d_sn_rowptr = nullptr, *d_sn_lptr = nullptr, *d_sn_uptr = nullptr;
+  std::vector<int64_t> uptr, invptr;
+  double* Lx = nullptr;
+  double* inv = nullptr;
+  double* arena[2] = {nullptr, nullptr};
+  int64_t arena_size[2] = {0, 0};
+  int* d_info = nullptr;
+  double* d_partial = nullptr;
+  Schedule fact;
+  std::vector<EntryMap> maps;
+  std::map<int, std::unique_ptr<SolvePlan>> plans;
+  bool factored = false;
+  size_t bytes = 0;
+  int64_t exported_nnz = 0;
+
+  DevSym devsym() const {
+    return DevSym{d_sn_first, d_sn_nrow, d_rows, d_rel, d_child_ptr, d_child_idx, d_sn_rowptr, d_sn_lptr, d_sn_uptr};
+  }
+};
+
+namespace slmm {
+
+static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena, const int64_t* d_vptr,
+                         int nrhs) {
+  const DevSym ds = h->devsym();
+  for (const Launch& L : sch.launches) {
+    switch (L.kind) {
+      case Launch::POTRF:
+        potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM>>>(sch.d_potrf + L.off, h->d_info);
+        break;
+      case Launch::GEMM_BIG:
+        gemm_tiles_kernel<128, 128, 2, 4><<<L.grid, 256, BIG_SMEM>>>(sch.d_gemm + L.off, L.count);
+        break;
+      case Launch::GEMM_SMALL:
+        gemm_tiles_kernel<64, 64, 2, 2><<<L.grid, 128, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
+        break;
+      case Launch::PULL_MAT:
+        extend_add_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
+                                                      h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
+        break;
+      case Launch::PULL_VEC:
+        vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, X, vec_arena[L.child_parity],
+                                                    vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
+        break;
+      default:
+        break;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_kind, Launch::Kind kind, int chunk) {
+  // lo_kind: 0 -> targets [0, ns)   1 -> targets [ns, ms)   2 -> targets [0, ms)
+  const int64_t off = (int64_t)sch.pull.size();
+  for (int q = S.level_ptr[level]; q < S.level_ptr[level + 1]; q++) {
+    const int p = S.level_sn[q];
+    if (S.child_ptr[p + 1] == S.child_ptr[p]) continue;
+    const int ns = S.sn_first[p + 1] - S.sn_first[p], ms = S.sn_nrow[p];
+    const int a = lo_kind == 1 ? ns : 0, b = lo_kind == 0 ? ns : ms;
+    // do not cross the ns boundary inside one item (the kernels branch on it per target)
+    for (int c0 = a; c0 < b;) {
+      int c1 = std::min(b, c0 + chunk);
+      if (c0 < ns && c1 > ns) c1 = ns;
+      sch.pull.push_back({p, c0, c1});
+      c0 = c1;
+    }
+  }
+  const int cnt = (int)(sch.pull.size() - off);
+  if (cnt > 0) sch.launches.push_back({kind, off, cnt, 0, (level + 1) & 1});
+}
+
+static void build_factor_schedule(slmm_chol* h) {
+  const Symbolic& S = h->S;
+  Schedule& sch = h->fact;
+  PhaseBuilder pb;
+  for (int d = S.nlevels - 1; d >= 0; d--) {
+    add_pull_items(sch, S, d, 0, Launch::PULL_MAT, 8);
+    int max_nib = 0;
+    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+      const int s = S.level_sn[q];
+      max_nib = std::max(max_nib, (S.sn_first[s + 1] - S.sn_first[s] + NBI - 1) / NBI);
+    }
+    for (int ph = 0; ph < 3 * max_nib; ph++) {
+      const int ib = ph / 3, kind = ph % 3;
+      for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+        const int s = S.level_sn[q];
+        const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
+        const int c0 = ib * NBI;
+        if (c0 >= ns) continue;
+        const int c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
+        double* P = h->Lx + S.sn_lptr[s];
+        double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
+        const int64_t ld = ms;
+        if (kind == 0) {
+          pb.potrf.push_back({P + c0 + c0 * ld, inv, (int32_t)ld, nb, f + c0, 0});
+          sch.flops += (double)nb * nb * nb / 3.0;
+        } else if (kind == 1) {
+          // rows below the diagonal block:  X = X * inv^T   (in place, one tile column)
+          pb.add(make_op(P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, inv, 1, NBI, ms - c1, nb, nb, 0));
+        } else {
+          const int ob0 = (c0 / NBO) * NBO, ob_end = std::min(ns, ob0 + NBO);
+          if (c1 < ob_end) {          // update the rest of the current outer block with this inner block
+            pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, ms - c1,
+                           ob_end - c1, nb, GF_LOWER | GF_ACCUM | GF_NEG));
+          } else if (c1 < ns) {       // outer block finished: update all remaining panel columns, K = block width
+            pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, ms - c1,
+                           ns - c1, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
+          } else if (rs > 0) {        // panel done: Schur complement  U = -L21 L21'
+            double* U = h->arena[d & 1] + h->uptr[s];
+            pb.add(make_op(U, 1, rs, P + ns, 1, ld, P + ns, 1, ld, rs, rs, ns, GF_LOWER | GF_NEG));
+          }
+        }
+      }
+      pb.flush(sch);
+    }
+    add_pull_items(sch, S, d, 1, Launch::PULL_MAT, 8);
+  }
+  sch.upload();
+}
+
+static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
+  auto it = h->plans.find(nrhs);
+  if (it != h->plans.end()) return it->second.get();
+  // keep at most two widths resident (probe block + deterministic RHS)
+  if (h->plans.size() >= 3) {
+    for (auto& kv : h->plans) kv.second->release();
+    h->plans.clear();
+  }
+  const Symbolic& S = h->S;
+  std::unique_ptr<SolvePlan> pl(new SolvePlan());
+  pl->nrhs = nrhs;
+  const int n = S.n;
+  pl->X = dev_alloc<double>((size_t)n * nrhs);
+  pl->X2 = dev_alloc<double>((size_t)n * nrhs);
+  std::vector<int64_t> vptr(S.nsuper, 0);
+  int64_t asz[2] = {0, 0};
+  for (int d = 0; d < S.nlevels; d++) {
+    int64_t off = 0;
+    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+      const int s = S.level_sn[q];
+      vptr[s] = off;
+      off += (int64_t)(S.sn_nrow[s] - (S.sn_first[s + 1] - S.sn_first[s])) * nrhs;
+    }
+    asz[d & 1] = std::max(asz[d & 1], off);
+  }
+  pl->arena[0] = dev_alloc<double>(asz[0]);
+  pl->arena[1] = dev_alloc<double>(asz[1]);
+  pl->d_vptr = dev_upload(vptr.data(), vptr.size());
+  pl->bytes = ((size_t)2 * n * nrhs + asz[0] + asz[1]) * 8;
+  const int64_t R = nrhs;
+  PhaseBuilder pb;
+  // ---------------- forward:  L y = b  (levels deepest first)
+  for (int d = S.nlevels - 1; d >= 0; d--) {
+    add_pull_items(pl->fwd, S, d, 0, Launch::PULL_VEC, 4);
+    int max_nib = 0;
+    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+      const int s = S.level_sn[q];
+      max_nib = std::max(max_nib, (S.sn_first[s + 1] - S.sn_first[s] + NBI - 1) / NBI);
+    }
+    for (int ph = 0; ph < 2 * max_nib + 1; ph++) {
+      for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+        const int s = S.level_sn[q];
+        const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
+        const int nib = (ns + NBI - 1) / NBI;
+        double* P = h->Lx + S.sn_lptr[s];
+        const int64_t ld = ms;
+        double* Xs = pl->X + (int64_t)f * R;
+        if (ph == 2 * nib) {                       // contribution block  u = -L21 y   (rs x nrhs)
+          if (rs > 0)
+            pb.add(make_op(pl->arena[d & 1] + vptr[s], 1, R, Xs, 1, R, P + ns, 1, ld, nrhs, rs, ns, GF_NEG));
+          continue;
+        }
+        if (ph > 2 * nib) continue;
+        const int ib = ph / 2, c0 = ib * NBI, c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
+        double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
+        if (ph % 2 == 0) {                         // y_b = inv * x_b        (transposed view: X^T = X^T inv^T)
+          pb.add(make_op(Xs + c0 * R, 1, R, Xs + c0 * R, 1, R, inv, 1, NBI, nrhs, nb, nb, 0));
+        } else if (c1 < ns) {                      // x[c1:ns] -= L[c1:ns, c0:c1] y_b
+          pb.add(make_op(Xs + c1 * R, 1, R, Xs + c0 * R, 1, R, P + c1 + c0 * ld, 1, ld, nrhs, ns - c1, nb,
+                         GF_ACCUM | GF_NEG));
+        }
+      }
+      pb.flush(pl->fwd);
+    }
+    add_pull_items(pl->fwd, S, d, 1, Launch::PULL_VEC, 4);
+  }
+  // ---------------- backward:  L' x = y  (roots first); reads ancestors' final rows through the row lists
+  for (int d = 0; d < S.nlevels; d++) {
+    int max_nib = 0;
+    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+      const int s = S.level_sn[q];
+      max_nib = std::max(max_nib, (S.sn_first[s + 1] - S.sn_first[s] + NBI - 1) / NBI);
+    }
+    for (int ph = 0; ph < 2 * max_nib + 1; ph++) {
+      for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+        const int s = S.level_sn[q];
+        const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
+        const int nib = (ns + NBI - 1) / NBI;
+        double* P = h->Lx + S.sn_lptr[s];
+        const int64_t ld = ms;
+        double* Xs = pl->X + (int64_t)f * R;
+        if (ph == 0) {                             // x_top -= L21' x[rows below]   (gathered rows)
+          if (rs > 0)
+            pb.add(make_op(Xs, 1, R, pl->X, 1, R, P + ns, ld, 1, nrhs, ns, rs, GF_ACCUM | GF_NEG,
+                           h->d_rows + S.sn_rowptr[s] + ns));
+          continue;
+        }
+        const int step = ph - 1, r = step / 2;     // blocks in reverse order
+        if (r >= nib) continue;
+        const int ib = nib - 1 - r, c0 = ib * NBI, c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
+        double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
+        if (step % 2 == 0) {                       // x_b = inv' * x_b
+          pb.add(make_op(Xs + c0 * R, 1, R, Xs + c0 * R, 1, R, inv, NBI, 1, nrhs, nb, nb, 0));
+        } else if (c0 > 0) {                       // x[0:c0] -= L[c0:c1, 0:c0]' x_b
+          pb.add(make_op(Xs, 1, R, Xs + c0 * R, 1, R, P + c0, ld, 1, nrhs, c0, nb, GF_ACCUM | GF_NEG));
+        }
+      }
+      pb.flush(pl->bwd);
+    }
+  }
+  // ---------------- L * Z  (same dataflow as the forward sweep, products instead of solves)
+  for (int d = S.nlevels - 1; d >= 0; d--) {
+    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+      const int s = S.level_sn[q];
+      const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
+      double* P = h->Lx + S.sn_lptr[s];
+      const int64_t ld = ms;
+      // out_top = L11 z_top (upper part of the diagonal block is stored as zeros)
+      pb.add(make_op(pl->X2 + (int64_t)f * R, 1, R, pl->X + (int64_t)f * R, 1, R, P, 1, ld, nrhs, ns, ns, 0));
+      if (rs > 0)
+        pb.add(make_op(pl->arena[d & 1] + vptr[s], 1, R, pl->X + (int64_t)f * R, 1, R, P + ns, 1, ld, nrhs, rs, ns, 0));
+    }
+    pb.flush(pl->lmul);
+    add_pull_items(pl->lmul, S, d, 2, Launch::PULL_VEC, 4);
+  }
+  pl->fwd.upload();
+  pl->bwd.upload();
+  pl->lmul.upload();
+  pl->bytes += pl->fwd.device_bytes() + pl->bwd.device_bytes() + pl->lmul.device_bytes();
+  SolvePlan* raw = pl.get();
+  h->plans[nrhs] = std::move(pl);
+  return raw;
+}
+
+}  // namespace slmm
+
+template <typename T>
+static void copy_out(T* dst, const std::vector<T>& v) { if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(T)); }
+
+// =========================================================================================================
+extern "C" {
+
+const char* slmm_last_error(void) { return slmm::last_error().c_str(); }
+int slmm_version(void) { return 100; }
+int slmm_device_count(int* out) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { c = 0; cudaGetLastError(); }
+  *out = c;
+  return SLMM_OK;
+}
+
+int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, int32_t ordering,
+                      const int32_t* user_perm, slmm_chol_t** out) {
+  SLMM_TRY
+  if (n <= 0 || !indptr || !indices || !out) throw std::invalid_argument("slmm_chol_analyze: bad arguments");
+  std::unique_ptr<slmm_chol> h(new slmm_chol());
+  SymbolicOptions opt;
+  opt.ordering = ordering;
+  analyze(n, indptr, indices, user_perm, opt, h->S);
+  const Symbolic& S = h->S;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    attr_set = true;
+  }
+  // update-matrix and inverse-slot offsets
+  h->uptr.assign(S.nsuper, 0);
+  h->invptr.assign(S.nsuper + 1, 0);
+  for (int d = 0; d < S.nlevels; d++) {
+    int64_t off = 0;
+    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
+      const int s = S.level_sn[q];
+      const int64_t rs = S.sn_nrow[s] - (S.sn_first[s + 1] - S.sn_first[s]);
+      h->uptr[s] = off;
+      off += rs * rs;
+    }
+    h->arena_size[d & 1] = std::max(h->arena_size[d & 1], off);
+  }
+  h->exported_nnz = 0;
+  for (int s = 0; s < S.nsuper; s++) {
+    const int64_t ns = S.sn_first[s + 1] - S.sn_first[s], ms = S.sn_nrow[s];
+    h->invptr[s + 1] = h->invptr[s] + ((ns + NBI - 1) / NBI) * NBI * NBI;
+    h->exported_nnz += ns * ms - ns * (ns - 1) / 2;
+  }
+  h->d_sn_first = dev_upload(S.sn_first.data(), S.sn_first.size());
+  h->d_sn_nrow = dev_upload(S.sn_nrow.data(), S.sn_nrow.size());
+  h->d_rows = dev_upload(S.rows.data(), S.rows.size());
+  h->d_rel = dev_upload(S.rel.data(), S.rel.size());
+  h->d_child_ptr = dev_upload(S.child_ptr.data(), S.child_ptr.size());
+  h->d_child_idx = dev_upload(S.child_idx.data(), S.child_idx.size());
+  h->d_col2sn = dev_upload(S.col2sn.data(), S.col2sn.size());
+  h->d_perm = dev_upload(S.perm.data(), S.perm.size());
+  h->d_sn_rowptr = dev_upload(S.sn_rowptr.data(), S.sn_rowptr.size());
+  h->d_sn_lptr = dev_upload(S.sn_lptr.data(), S.sn_lptr.size());
+  h->d_sn_uptr = dev_upload(h->uptr.data(), h->uptr.size());
+  h->Lx = dev_alloc<double>(S.lsize);
+  h->inv = dev_alloc<double>(h->invptr[S.nsuper]);
+  h->arena[0] = dev_alloc<double>(h->arena_size[0]);
+  h->arena[1] = dev_alloc<double>(h->arena_size[1]);
+  h->d_info = dev_alloc<int>(1);
+  h->d_partial = dev_alloc<double>(1024);
+  CUDA_OK(cudaMemset(h->Lx, 0, S.lsize * sizeof(double)));
+  build_factor_schedule(h.get());
+  h->bytes = (S.lsize + h->invptr[S.nsuper] + h->arena_size[0] + h->arena_size[1]) * 8 +
+             (S.rows.size() * 2 + S.sn_first.size() * 8) * 4 + h->fact.device_bytes();
+  CUDA_OK(cudaDeviceSynchronize());
+  *out = h.release();
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_destroy(slmm_chol_t* h) {
+  if (!h) return SLMM_OK;
+  dev_free(h->d_sn_first); dev_free(h->d_sn_nrow); dev_free(h->d_rows); dev_free(h->d_rel);
+  dev_free(h->d_child_ptr); dev_free(h->d_child_idx); dev_free(h->d_col2sn); dev_free(h->d_perm);
+  dev_free(h->d_sn_rowptr); dev_free(h->d_sn_lptr); dev_free(h->d_sn_uptr);
+  dev_free(h->Lx); dev_free(h->inv); dev_free(h->arena[0]); dev_free(h->arena[1]);
+  dev_free(h->d_info); dev_free(h->d_partial);
+  h->fact.release();
+  for (auto& m : h->maps) dev_free(m.d_map);
+  for (auto& kv : h->plans) kv.second->release();
+  delete h;
+  return SLMM_OK;
+}
+
+int slmm_chol_stats(const slmm_chol_t* h, int64_t* i, double* d) {
+  SLMM_TRY
+  if (!h) throw std::invalid_argument("null handle");
+  const Symbolic& S = h->S;
+  if (i) {
+    i[0] = S.n; i[1] = S.nsuper; i[2] = S.nlevels; i[3] = S.nnzL; i[4] = S.lsize; i[5] = h->exported_nnz;
+    i[6] = S.max_front_rows; i[7] = S.max_super_cols; i[8] = S.ncomponents;
+    i[9] = (int64_t)h->fact.launches.size();
+    size_t b = h->bytes;
+    for (auto& kv : h->plans) b += kv.second->bytes;
+    for (auto& m : h->maps) b += m.nnz * 8;
+    i[10] = (int64_t)b;
+  }
+  if (d) { d[0] = S.flops; d[1] = S.t_order; d[2] = S.t_symbolic; d[3] = h->fact.flops; }
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_perm(const slmm_chol_t* h, int32_t* perm) {
+  SLMM_TRY
+  if (!h || !perm) throw std::invalid_argument("null argument");
+  memcpy(perm, h->S.perm.data(), sizeof(int32_t) * h->S.n);
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_register_pattern(slmm_chol_t* h, const int32_t* indptr, const int32_t* indices, int32_t* map_id) {
+  SLMM_TRY
+  if (!h || !indptr || !indices || !map_id) throw std::invalid_argument("null argument");
+  const int64_t nnz = indptr[h->S.n];
+  std::vector<int64_t> tgt(nnz);
+  entry_map(h->S, indptr, indices, tgt.data());
+  EntryMap m;
+  m.nnz = nnz;
+  m.d_map = dev_upload(tgt.data(), tgt.size());
+  CUDA_OK(cudaDeviceSynchronize());
+  h->maps.push_back(m);
+  *map_id = (int32_t)h->maps.size() - 1;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_add_values(slmm_chol_t* h, int32_t map_id, const double* d_values, double sigma, int32_t first) {
+  SLMM_TRY
+  if (!h || map_id < 0 || map_id >= (int)h->maps.size()) throw std::invalid_argument("bad map id");
+  if (first) CUDA_OK(cudaMemsetAsync(h->Lx, 0, h->S.lsize * sizeof(double), 0));
+  const EntryMap& m = h->maps[map_id];
+  if (m.nnz > 0) {
+    const int grid = (int)std::min<int64_t>((m.nnz + 255) / 256, 148 * 16);
+    scatter_axpy_kernel<<<grid, 256>>>(m.d_map, d_values, sigma, h->Lx, m.nnz);
+  }
+  CUDA_OK(cudaGetLastError());
+  h->factored = false;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_factorize(slmm_chol_t* h, int32_t* fail_col) {
+  SLMM_TRY
+  if (!h) throw std::invalid_argument("null handle");
+  const int big = 0x7fffffff;
+  CUDA_OK(cudaMemcpyAsync(h->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, 0));
+  run_schedule(h, h->fact, nullptr, nullptr, nullptr, 0);
+  int info = 0;
+  CUDA_OK(cudaMemcpy(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+  if (info != big) {
+    if (fail_col) *fail_col = info - 1;
+    set_last_error("matrix is not positive definite (non-positive pivot at permuted column " + std::to_string(info - 1) + ")");
+    return SLMM_ERR_NOT_POSDEF;
+  }
+  if (fail_col) *fail_col = -1;
+  h->factored = true;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_logdet(slmm_chol_t* h, double* out) {
+  SLMM_TRY
+  if (!h || !out) throw std::invalid_argument("null argument");
+  if (!h->factored) throw std::invalid_argument("factorize first");
+  const int grid = std::min(1024, (h->S.n + 255) / 256);
+  logdet_kernel<<<grid, 256>>>(h->Lx, h->d_col2sn, h->d_sn_first, h->d_sn_nrow, h->d_sn_lptr, h->S.n, h->d_partial);
+  std::vector<double> part(grid);
+  CUDA_OK(cudaMemcpy(part.data(), h->d_partial, grid * sizeof(double), cudaMemcpyDeviceToHost));
+  double s = 0;
+  for (double v : part) s += v;
+  *out = 2.0 * s;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_solve(slmm_chol_t* h, double* d_B, int32_t nrhs, int32_t mode) {
+  SLMM_TRY
+  if (!h || !d_B || nrhs <= 0) throw std::invalid_argument("bad arguments");
+  if (!h->factored) throw std::invalid_argument("factorize first");
+  SolvePlan* pl = get_plan(h, nrhs);
+  const int n = h->S.n;
+  const int64_t total = (int64_t)n * nrhs;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  gather_rows_kernel<<<grid, 256>>>(d_B, pl->X, h->d_perm, n, nrhs, 0);
+  if (mode == 0 || mode == 1) run_schedule(h, pl->fwd, pl->X, pl->arena, pl->d_vptr, nrhs);
+  if (mode == 0 || mode == 2) run_schedule(h, pl->bwd, pl->X, pl->arena, pl->d_vptr, nrhs);
+  gather_rows_kernel<<<grid, 256>>>(pl->X, d_B, h->d_perm, n, nrhs, 1);
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrhs) {
+  SLMM_TRY
+  if (!h || !d_Z || !d_out || nrhs <= 0) throw std::invalid_argument("bad arguments");
+  if (!h->factored) throw std::invalid_argument("factorize first");
+  SolvePlan* pl = get_plan(h, nrhs);
+  const int n = h->S.n;
+  const int64_t total = (int64_t)n * nrhs;
+  CUDA_OK(cudaMemcpyAsync(pl->X, d_Z, total * sizeof(double), cudaMemcpyDeviceToDevice, 0));
+  run_schedule(h, pl->lmul, pl->X2, pl->arena, pl->d_vptr, nrhs);
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  gather_rows_kernel<<<grid, 256>>>(pl->X2, d_out, h->d_perm, n, nrhs, 1);
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_export_L(slmm_chol_t* h, int64_t* colptr, int32_t* rowidx, double* values) {
+  SLMM_TRY
+  if (!h || !colptr || !rowidx || !values) throw std::invalid_argument("null argument");
+  if (!h->factored) throw std::invalid_argument("factorize first");
+  const Symbolic& S = h->S;
+  std::vector<double> Lh(S.lsize);
+  CUDA_OK(cudaMemcpy(Lh.data(), h->Lx, S.lsize * sizeof(double), cudaMemcpyDeviceToHost));
+  int64_t q = 0;
+  for (int s = 0; s < S.nsuper; s++) {
+    const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s];
+    const int32_t* rows = S.rows.data() + S.sn_rowptr[s];
+    const double* P = Lh.data() + S.sn_lptr[s];
+    for (int c = 0; c < ns; c++) {
+      colptr[f + c] = q;
+      for (int r = c; r < ms; r++) { rowidx[q] = rows[r]; values[q] = P[r + (int64_t)c * ms]; q++; }
+    }
+  }
+  colptr[S.n] = q;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+struct slmm_symbolic { Symbolic S; };
+
+int slmm_symbolic_create(int32_t n, const int32_t* indptr, const int32_t* indices, int32_t ordering,
+                         const int32_t* user_perm, slmm_symbolic_t** out) {
+  SLMM_TRY
+  if (n <= 0 || !indptr || !indices || !out) throw std::invalid_argument("slmm_symbolic_create: bad arguments");
+  std::unique_ptr<slmm_symbolic> h(new slmm_symbolic());
+  SymbolicOptions opt;
+  opt.ordering = ordering;
+  analyze(n, indptr, indices, user_perm, opt, h->S);
+  *out = h.release();
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_symbolic_destroy(slmm_symbolic_t* s) { delete s; return SLMM_OK; }
+
+int slmm_symbolic_stats(const slmm_symbolic_t* h, int64_t* i, double* d) {
+  SLMM_TRY
+  if (!h) throw std::invalid_argument("null handle");
+  const Symbolic& S = h->S;
+  if (i) {
+    int64_t exported = 0;
+    for (int s = 0; s < S.nsuper; s++) {
+      const int64_t ns = S.sn_first[s + 1] - S.sn_first[s], ms = S.sn_nrow[s];
+      exported += ns * ms - ns * (ns - 1) / 2;
+    }
+    i[0] = S.n; i[1] = S.nsuper; i[2] = S.nlevels; i[3] = S.nnzL; i[4] = S.lsize; i[5] = exported;
+    i[6] = S.max_front_rows; i[7] = S.max_super_cols; i[8] = S.ncomponents; i[9] = (int64_t)S.rows.size();
+  }
+  if (d) { d[0] = S.flops; d[1] = S.t_order; d[2] = S.t_symbolic; d[3] = 0; }
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_symbolic_arrays(const slmm_symbolic_t* h, int32_t* perm, int32_t* parent, int32_t* colcount,
+                         int32_t* sn_first, int32_t* sn_nrow, int32_t* sn_parent, int64_t* sn_rowptr,
+                         int64_t* sn_lptr, int32_t* rows, int32_t* rel, int32_t* level_ptr, int32_t* level_sn) {
+  SLMM_TRY
+  if (!h) throw std::invalid_argument("null handle");
+  const Symbolic& S = h->S;
+  copy_out(perm, S.perm); copy_out(parent, S.parent); copy_out(colcount, S.colcount);
+  copy_out(sn_first, S.sn_first); copy_out(sn_nrow, S.sn_nrow); copy_out(sn_parent, S.sn_parent);
+  copy_out(sn_rowptr, S.sn_rowptr); copy_out(sn_lptr, S.sn_lptr); copy_out(rows, S.rows); copy_out(rel, S.rel);
+  copy_out(level_ptr, S.level_ptr); copy_out(level_sn, S.level_sn);
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_symbolic_entry_map(const slmm_symbolic_t* h, const int32_t* indptr, const int32_t* indices, int64_t* target) {
+  SLMM_TRY
+  if (!h || !indptr || !indices || !target) throw std::invalid_argument("null argument");
+  entry_map(h->S, indptr, indices, target);
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,
+                       int32_t lower, int32_t reps, float* ms_out) {
+  SLMM_TRY
+  CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+  Schedule sch;
+  PhaseBuilder pb;
+  pb.add(make_op(d_C, 1, M, d_A, 1, M, d_B, 1, N, M, N, K, lower ? GF_LOWER : 0));
+  pb.flush(sch);
+  sch.upload();
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  slmm_chol dummy;
+  run_schedule(&dummy, sch, nullptr, nullptr, nullptr, 0);
+  CUDA_OK(cudaEventRecord(e0, 0));
+  for (int r = 0; r < reps; r++) run_schedule(&dummy, sch, nullptr, nullptr, nullptr, 0);
+  CUDA_OK(cudaEventRecord(e1, 0));
+  CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = reps > 0 ? ms / reps : 0.f;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  sch.release();
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+// HBM-bound CSR kernels of the path: Haseman-Elston moments (SpMV-dot + sparse Hadamard dot-reductions),
+// SpMM, and SpMM fused with the column-wise quadratic-form reduction.
+// Replaces scipy's csr_matvec / csr_matvecs / csr_elmult_csr on the call sites
+// reference scilmm/SparseCholesky.py:65,66,70 (compute_gradients), :157,:161 (compute_hess), :223,:229 (HE).
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+
+namespace slmm {
+
+constexpr int MAXK = 8;
+
+struct CsrDev {
+  const int32_t* indptr = nullptr;
+  const int32_t* indices = nullptr;
+  const double* data = nullptr;
+  int64_t nnz = 0;
+  int pattern = -1;       // index of the first matrix with this pattern
+  bool owned_pattern = false, owned_data = false;
+  std::vector<int32_t> h_indptr;   // kept for pattern comparison (uploaded matrices only)
+  uint64_t idx_hash = 0;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One pass over a group of G matrices sharing one sparsity pattern: warp per row, lanes stride the row
+// (coalesced index/value streams, y gathered through L2).  Per-lane partial sums live in registers across all
+// rows of the warp; a single shuffle reduction per warp at the end, then per-CTA partials (deterministic).
+//   q_off[g]  += a_g(i,j) y_i y_j      (i != j)        q_diag[g]  += a_g(i,i) y_i^2
+//   S_off[g,h]+= a_g(i,j) a_h(i,j)     (i != j)        S_diag[g,h]+= a_g(i,i) a_h(i,i)
+template <int G>
+struct GroupArgs {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const double* data[G];
+};
+
+template <int G>
+__global__ void __launch_bounds__(256) he_group_kernel(GroupArgs<G> a, const double* __restrict__ y, int row_begin,
+                                                       int row_end, double* __restrict__ partial) {
+  constexpr int NP = G * (G + 1) / 2;
+  constexpr int NV = 2 * G + 2 * NP;
+  double qo[G], qd[G], so[NP], sd[NP];
+#pragma unroll
+  for (int g = 0; g < G; g++) qo[g] = qd[g] = 0.0;
+#pragma unroll
+  for (int p = 0; p < NP; p++) so[p] = sd[p] = 0.0;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    const int b = a.indptr[row], e = a.indptr[row + 1];
+    const double yi = y[row];
+    double rowacc[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) rowacc[g] = 0.0;
+    for (int p = b + lane; p < e; p += 32) {
+      const int col = a.indices[p];
+      const double yj = y[col];
+      double v[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) v[g] = a.data[g][p];
+      if (col != row) {
+#pragma unroll
+        for (int g = 0; g < G; g++) rowacc[g] += v[g] * yj;
+        int q = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int h = 0; h <= g; h++) so[q++] += v[g] * v[h];
+      } else {
+        int q = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          qd[g] += v[g] * yi * yi;
+#pragma unroll
+          for (int h = 0; h <= g; h++) sd[q++] += v[g] * v[h];
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) qo[g] += rowacc[g] * yi;
+  }
+  __shared__ double sh[8][NV];
+  const int warp = threadIdx.x >> 5;
+  double vals[NV];
+#pragma unroll
+  for (int g = 0; g < G; g++) { vals[g] = qo[g]; vals[G + g] = qd[g]; }
+#pragma unroll
+  for (int p = 0; p < NP; p++) { vals[2 * G + p] = so[p]; vals[2 * G + NP + p] = sd[p]; }
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const double s = warp_sum(vals[k]);
+    if (lane == 0) sh[warp][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+// Hadamard dot of two matrices with different patterns: warp per row, lanes walk the shorter row and binary
+// search the longer one (sorted indices).  out: [off, diag] partials per CTA.
+__global__ void __launch_bounds__(256) he_cross_kernel(const int32_t* __restrict__ ap, const int32_t* __restrict__ ai,
+                                                       const double* __restrict__ ax, const int32_t* __restrict__ bp,
+                                                       const int32_t* __restrict__ bi, const double* __restrict__ bx,
+                                                       int row_begin, int row_end, double* __restrict__ partial) {
+  double off = 0.0, dg = 0.0;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    int sb = ap[row], se = ap[row + 1], lb = bp[row], le = bp[row + 1];
+    const int32_t *si = ai, *li = bi;
+    const double *sx = ax, *lx = bx;
+    if (se - sb > le - lb) {
+      int t = sb; sb = lb; lb = t; t = se; se = le; le = t;
+      si = bi; li = ai; sx = bx; lx = ax;
+    }
+    for (int p = sb + lane; p < se; p += 32) {
+      const int col = si[p];
+      int lo = lb, hi = le;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (li[mid] < col) lo = mid + 1; else hi = mid; }
+      if (lo < le && li[lo] == col) {
+        const double v = sx[p] * lx[lo];
+        if (col == row) dg += v; else off += v;
+      }
+    }
+  }
+  __shared__ double sh[8][2];
+  const int warp = threadIdx.x >> 5;
+  off = warp_sum(off);
+  dg = warp_sum(dg);
+  if (lane == 0) { sh[warp][0] = off; sh[warp][1] = dg; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+// final deterministic reduction of per-CTA partials: dst[map[k]] (+)= sum_b partial[b*nv + k]
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblocks, int nv,
+                                       const int32_t* __restrict__ dst_index, double* __restrict__ dst) {
+  const int k = blockIdx.x;
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * nv + k];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int d = dst_index ? dst_index[k] : k;
+    if (d >= 0) dst[d] = sh[0];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SpMM on C-ordered blocks: out[i,:] = sum_j A[i,j] X[j,:].  A warp owns a row; lanes own columns
+// (each X row is contiguous, so every gathered row is a coalesced read).  CPL = columns per lane.
+template <int CPL, bool DOT>
+__global__ void __launch_bounds__(256) spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                   const double* __restrict__ data, const double* __restrict__ X, int ncols,
+                                                   int row_begin, int row_end, double* __restrict__ out,
+                                                   double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  double dot[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; c++) dot[c] = 0.0;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    double acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) acc[c] = 0.0;
+    for (int p0 = b; p0 < e; p0 += 32) {
+      // stage up to 32 (col, val) pairs in registers, then broadcast them one at a time
+      const int pl = p0 + lane;
+      const int mycol = pl < e ? indices[pl] : 0;
+      const double myval = pl < e ? data[pl] : 0.0;
+      const int cnt = min(32, e - p0);
+      for (int k = 0; k < cnt; k++) {
+        const int col = __shfl_sync(0xffffffffu, mycol, k);
+        const double v = __shfl_sync(0xffffffffu, myval, k);
+        const double* xr = X + (int64_t)col * ncols;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+          const int j = lane + 32 * c;
+          if (j < ncols) acc[c] += v * xr[j];
+        }
+      }
+    }
+    if (DOT) {
+      const double* xi = X + (int64_t)row * ncols;
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const int j = lane + 32 * c;
+        if (j < ncols) dot[c] += acc[c] * xi[j];
+      }
+    } else {
+      double* orow = out + (int64_t)row * ncols;
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const int j = lane + 32 * c;
+        if (j < ncols) orow[j] = acc[c];
+      }
+    }
+  }
+  if (DOT) {
+    __shared__ double sh[8][32 * CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) sh[warp][lane + 32 * c] = dot[c];
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncols; j += 256) {
+      double s = 0.0;
+      for (int w = 0; w < 8; w++) s += sh[w][j];
+      partial[(int64_t)blockIdx.x * ncols + j] = s;
+    }
+  }
+}
+
+}  // namespace slmm
+
+using namespace slmm;
+
+struct slmm_matset {
+  int n = 0, K = 0;
+  std::vector<CsrDev> m;
+  double* d_partial = nullptr;
+  size_t partial_cap = 0;
+  double* d_y = nullptr;
+  double* d_out = nullptr;
+  int32_t* d_dst = nullptr;
+  double* partial(size_t count) {
+    if (count > partial_cap) {
+      dev_free(d_partial);
+      d_partial = dev_alloc<double>(count);
+      partial_cap = count;
+    }
+    return d_partial;
+  }
+};
+
+namespace slmm {
+
+static uint64_t hash_bytes(const void* p, size_t nbytes) {
+  const uint64_t* w = (const uint64_t*)p;
+  uint64_t h = 1469598103934665603ull;
+  size_t nw = nbytes / 8;
+  for (size_t i = 0; i < nw; i++) { h ^= w[i]; h *= 1099511628211ull; h ^= h >> 29; }
+  const unsigned char* b = (const unsigned char*)p + nw * 8;
+  for (size_t i = 0; i < nbytes % 8; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+static int he_grid(int rows) {
+  const int warps_needed = std::max(1, rows);
+  return std::max(1, std::min(148 * 8, (warps_needed + 7) / 8));
+}
+
+template <int G>
+static void launch_group(slmm_matset* ms, const int* members, const double* d_y, int r0, int r1, double* d_out) {
+  const int K = ms->K;
+  constexpr int NP = G * (G + 1) / 2, NV = 2 * G + 2 * NP;
+  GroupArgs<G> a;
+  a.indptr = ms->m[members[0]].indptr;
+  a.indices = ms->m[members[0]].indices;
+  for (int g = 0; g < G; g++) a.data[g] = ms->m[members[g]].data;
+  const int grid = he_grid(r1 - r0);
+  double* part = ms->partial((size_t)grid * NV);
+  he_group_kernel<G><<<grid, 256>>>(a, d_y, r0, r1, part);
+  // destination indices inside [q_off | q_diag | S_off | S_diag]
+  std::vector<int32_t> dst(NV);
+  for (int g = 0; g < G; g++) { dst[g] = members[g]; dst[G + g] = K + members[g]; }
+  int q = 0;
+  for (int g = 0; g < G; g++)
+    for (int h = 0; h <= g; h++) {
+      dst[2 * G + q] = 2 * K + members[g] * K + members[h];
+      dst[2 * G + NP + q] = 2 * K + K * K + members[g] * K + members[h];
+      q++;
+    }
+  CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst.data(), NV * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+  reduce_partials_kernel<<<NV, 256>>>(part, grid, NV, ms->d_dst, d_out);
+  // the copy above must not be overwritten by the next group before the kernel ran: d_dst is consumed in
+  // stream order and the next memcpy is also stream-ordered (pageable source is staged synchronously).
+}
+
+}  // namespace slmm
+
+extern "C" {
+
+int slmm_matset_create(int32_t n, int32_t K, slmm_matset_t** out) {
+  SLMM_TRY
+  if (n <= 0 || K <= 0 || K > MAXK || !out) throw std::invalid_argument("slmm_matset_create: need 0 < K <= 8, n > 0");
+  std::unique_ptr<slmm_matset> ms(new slmm_matset());
+  ms->n = n;
+  ms->K = K;
+  ms->m.resize(K);
+  ms->d_y = dev_alloc<double>(n);
+  ms->d_out = dev_alloc<double>(2 * K + 2 * K * K);
+  ms->d_dst = dev_alloc<int32_t>(64);
+  *out = ms.release();
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_destroy(slmm_matset_t* ms) {
+  if (!ms) return SLMM_OK;
+  for (auto& c : ms->m) {
+    if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
+    if (c.owned_data) dev_free((void*)c.data);
+  }
+  dev_free(ms->d_partial); dev_free(ms->d_y); dev_free(ms->d_out); dev_free(ms->d_dst);
+  delete ms;
+  return SLMM_OK;
+}
+
+int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* indptr, const int32_t* indices, const double* data) {
+  SLMM_TRY
+  if (!ms || k < 0 || k >= ms->K || !indptr || !indices || !data) throw std::invalid_argument("bad arguments");
+  CsrDev& c = ms->m[k];
+  if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
+  if (c.owned_data) dev_free((void*)c.data);
+  c = CsrDev();
+  const int n = ms->n;
+  c.nnz = indptr[n];
+  c.h_indptr.assign(indptr, indptr + n + 1);
+  c.idx_hash = hash_bytes(indices, (size_t)c.nnz * 4);
+  c.pattern = k;
+  for (int j = 0; j < ms->K; j++) {
+    const CsrDev& o = ms->m[j];
+    if (j == k || o.pattern != j || o.nnz != c.nnz || o.h_indptr.empty() || o.idx_hash != c.idx_hash) continue;
+    if (memcmp(o.h_indptr.data(), indptr, sizeof(int32_t) * (n + 1)) == 0) { c.pattern = j; break; }
+  }
+  if (c.pattern == k) {
+    c.indptr = dev_upload(indptr, n + 1);
+    c.indices = dev_upload(indices, c.nnz);
+    c.owned_pattern = true;
+  } else {
+    c.indptr = ms->m[c.pattern].indptr;
+    c.indices = ms->m[c.pattern].indices;
+  }
+  c.data = dev_upload(data, c.nnz);
+  c.owned_data = true;
+  CUDA_OK(cudaStreamSynchronize(0));
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indptr, const int32_t* d_indices,
+                            const double* d_data, int64_t nnz, int32_t same_as) {
+  SLMM_TRY
+  if (!ms || k < 0 || k >= ms->K || !d_indptr || !d_indices || !d_data) throw std::invalid_argument("bad arguments");
+  if (same_as >= ms->K || same_as == k) throw std::invalid_argument("bad same_as");
+  CsrDev& c = ms->m[k];
+  if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
+  if (c.owned_data) dev_free((void*)c.data);
+  c = CsrDev();
+  c.indptr = d_indptr; c.indices = d_indices; c.data = d_data; c.nnz = nnz;
+  c.pattern = same_as >= 0 ? ms->m[same_as].pattern : k;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_nnz(const slmm_matset_t* ms, int32_t k, int64_t* out) {
+  if (!ms || k < 0 || k >= ms->K || !out) return SLMM_ERR_INVALID;
+  *out = ms->m[k].nnz;
+  return SLMM_OK;
+}
+
+int slmm_matset_values(const slmm_matset_t* ms, int32_t k, const double** out) {
+  if (!ms || k < 0 || k >= ms->K || !out) return SLMM_ERR_INVALID;
+  *out = ms->m[k].data;
+  return SLMM_OK;
+}
+
+int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1, double* d_out) {
+  SLMM_TRY
+  if (!ms || !d_y || !d_out) throw std::invalid_argument("null argument");
+  const int K = ms->K;
+  if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
+  for (int k = 0; k < K; k++)
+    if (!ms->m[k].data) throw std::invalid_argument("matrix not set");
+  CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * (2 * K + 2 * K * K), 0));
+  // pattern groups
+  std::vector<char> done(K, 0);
+  for (int k = 0; k < K; k++) {
+    if (done[k]) continue;
+    int members[MAXK], G = 0;
+    for (int j = k; j < K; j++)
+      if (!done[j] && ms->m[j].pattern == ms->m[k].pattern) { members[G++] = j; done[j] = 1; }
+    for (int g0 = 0; g0 < G; g0 += 4) {           // at most 4 matrices fused per pass
+      const int gn = std::min(4, G - g0);
+      switch (gn) {
+        case 1: launch_group<1>(ms, members + g0, d_y, r0, r1, d_out); break;
+        case 2: launch_group<2>(ms, members + g0, d_y, r0, r1, d_out); break;
+        case 3: launch_group<3>(ms, members + g0, d_y, r0, r1, d_out); break;
+        default: launch_group<4>(ms, members + g0, d_y, r0, r1, d_out); break;
+      }
+    }
+  }
+  // pairs that were not covered by a fused pass
+  for (int i = 0; i < K; i++)
+    for (int j = 0; j < i; j++) {
+      bool fused = false;
+      if (ms->m[i].pattern == ms->m[j].pattern) {
+        // same group: fused only if they fell into the same chunk of 4
+        int pi = 0, pj = 0, c = 0;
+        for (int t = 0; t < K; t++)
+          if (ms->m[t].pattern == ms->m[i].pattern) { if (t == i) pi = c; if (t == j) pj = c; c++; }
+        fused = (pi / 4 == pj / 4);
+      }
+      if (fused) continue;
+      const int grid = he_grid(r1 - r0);
+      double* part = ms->partial((size_t)grid * 2);
+      he_cross_kernel<<<grid, 256>>>(ms->m[i].indptr, ms->m[i].indices, ms->m[i].data, ms->m[j].indptr,
+                                     ms->m[j].indices, ms->m[j].data, r0, r1, part);
+      const int32_t dst[2] = {2 * K + i * K + j, 2 * K + K * K + i * K + j};
+      CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
+      reduce_partials_kernel<<<2, 256>>>(part, grid, 2, ms->d_dst, d_out);
+    }
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_he_moments_host(slmm_matset_t* ms, const double* h_y, double* h_out) {
+  SLMM_TRY
+  if (!ms || !h_y || !h_out) throw std::invalid_argument("null argument");
+  CUDA_OK(cudaMemcpyAsync(ms->d_y, h_y, sizeof(double) * ms->n, cudaMemcpyHostToDevice, 0));
+  int rc = slmm_he_moments(ms, ms->d_y, 0, ms->n, ms->d_out);
+  if (rc != SLMM_OK) return rc;
+  CUDA_OK(cudaMemcpy(h_out, ms->d_out, sizeof(double) * (2 * ms->K + 2 * ms->K * ms->K), cudaMemcpyDeviceToHost));
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+static int spmm_impl(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, int32_t r0, int32_t r1,
+                     double* d_out, bool dot) {
+  if (!ms || k < 0 || k >= ms->K || !d_X || !d_out || ncols <= 0) throw std::invalid_argument("bad arguments");
+  if (ncols > 256) throw std::invalid_argument("at most 256 columns per call");
+  if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
+  const CsrDev& c = ms->m[k];
+  if (!c.data) throw std::invalid_argument("matrix not set");
+  const int grid = he_grid(r1 - r0);
+  double* part = dot ? ms->partial((size_t)grid * ncols) : nullptr;
+  const int cpl = (ncols + 31) / 32;
+#define SPMM_CASE(C)                                                                                                  \
+  if (dot) spmm_kernel<C, true><<<grid, 256>>>(c.indptr, c.indices, c.data, d_X, ncols, r0, r1, nullptr, part);       \
+  else spmm_kernel<C, false><<<grid, 256>>>(c.indptr, c.indices, c.data, d_X, ncols, r0, r1, d_out, nullptr);
+  if (cpl <= 1) { SPMM_CASE(1) }
+  else if (cpl <= 2) { SPMM_CASE(2) }
+  else if (cpl <= 4) { SPMM_CASE(4) }
+  else { SPMM_CASE(8) }
+#undef SPMM_CASE
+  if (dot) reduce_partials_kernel<<<ncols, 256>>>(part, grid, ncols, nullptr, d_out);
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+}
+
+int slmm_spmm(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, double* d_out) {
+  SLMM_TRY
+  return spmm_impl(ms, k, d_X, ncols, 0, ms ? ms->n : 0, d_out, false);
+  SLMM_CATCH
+}
+
+int slmm_spmm_coldot(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, int32_t r0, int32_t r1,
+                     double* d_out) {
+  SLMM_TRY
+  return spmm_impl(ms, k, d_X, ncols, r0, r1, d_out, true);
+  SLMM_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+"""Thin Python objects over the C-ABI handles.  torch is used only to own device memory and for the
+tiny dense c x c / n x c algebra around the kernels; every sparse / factorization kernel is in
+libscilmm_b200.so.  Nothing here computes on the CPU in place of a kernel."""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import check, lib, np_ptr
+
+ORDERINGS = {"natural": 0, "given": 1, "metis": 2, "nesdis": 2, "default": 2, "amd": 3, "mindeg": 3}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("scilmm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def device_count():
+    c = C.c_int(0)
+    check(lib().slmm_device_count(C.byref(c)))
+    return c.value
+
+
+def _as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def canonical_csr(m):
+    """scipy CSR with sorted int32 indices and float64 data (the layout the reference hands scipy)."""
+    m = sp.csr_matrix(m)
+    if not m.has_sorted_indices:
+        m = m.sorted_indices()
+    if m.indices.dtype != np.int32 or m.indptr.dtype != np.int32:
+        m = sp.csr_matrix((m.data, m.indices.astype(np.int32), m.indptr.astype(np.int32)), shape=m.shape)
+    if m.data.dtype != np.float64:
+        m = m.astype(np.float64)
+    return m
+
+
+def to_device(a, torch=None):
+    """Host ndarray -> CUDA tensor through pinned staging (fast H2D)."""
+    torch = torch or require_cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    try:
+        t = t.pin_memory()
+    except RuntimeError:
+        pass
+    return t.to("cuda", non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------------ symbolic
+class SymbolicView(object):
+    """Host-only symbolic analysis (no GPU needed)."""
+
+    def __init__(self, pattern, ordering="metis", perm=None):
+        pattern = canonical_csr(pattern)
+        n = pattern.shape[0]
+        h = C.c_void_p()
+        self._perm_in = None if perm is None else _as_i32(perm)
+        code = ORDERINGS[ordering] if perm is None else 1
+        check(lib().slmm_symbolic_create(n, np_ptr(pattern.indptr), np_ptr(pattern.indices), code,
+                                         None if perm is None else np_ptr(self._perm_in), C.byref(h)))
+        self._h = h
+        self.n = n
+        i = np.zeros(16, dtype=np.int64)
+        d = np.zeros(8, dtype=np.float64)
+        check(lib().slmm_symbolic_stats(h, np_ptr(i), np_ptr(d)))
+        self.nsuper, self.nlevels, self.nnzL, self.lsize = int(i[1]), int(i[2]), int(i[3]), int(i[4])
+        self.exported_nnz, self.max_front_rows, self.max_super_cols = int(i[5]), int(i[6]), int(i[7])
+        self.ncomponents, self.total_rows = int(i[8]), int(i[9])
+        self.flops, self.t_order, self.t_symbolic = float(d[0]), float(d[1]), float(d[2])
+
+    def arrays(self):
+        n, ns = self.n, self.nsuper
+        out = dict(perm=np.zeros(n, np.int32), parent=np.zeros(n, np.int32), colcount=np.zeros(n, np.int32),
+                   sn_first=np.zeros(ns + 1, np.int32), sn_nrow=np.zeros(ns, np.int32),
+                   sn_parent=np.zeros(ns, np.int32), sn_rowptr=np.zeros(ns + 1, np.int64),
+                   sn_lptr=np.zeros(ns + 1, np.int64), rows=np.zeros(self.total_rows, np.int32),
+                   rel=np.zeros(self.total_rows, np.int32), level_ptr=np.zeros(self.nlevels + 1, np.int32),
+                   level_sn=np.zeros(ns, np.int32))
+        order = ["perm", "parent", "colcount", "sn_first", "sn_nrow", "sn_parent", "sn_rowptr", "sn_lptr", "rows",
+                 "rel", "level_ptr", "level_sn"]
+        check(lib().slmm_symbolic_arrays(self._h, *[np_ptr(out[k]) for k in order]))
+        return out
+
+    def entry_map(self, pattern):
+        pattern = canonical_csr(pattern)
+        tgt = np.zeros(pattern.nnz, dtype=np.int64)
+        check(lib().slmm_symbolic_entry_map(self._h, np_ptr(pattern.indptr), np_ptr(pattern.indices), np_ptr(tgt)))
+        return tgt
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().slmm_symbolic_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ matrices
+class MatSet(object):
+    """K CSR relationship matrices resident in HBM (slmm_matset_t)."""
+
+    def __init__(self, mats):
+        torch = require_cuda()
+        mats = [canonical_csr(m) for m in mats]
+        self.n = mats[0].shape[0]
+        self.K = len(mats)
+        h = C.c_void_p()
+        check(lib().slmm_matset_create(self.n, self.K, C.byref(h)))
+        self._h = h
+        self._keep = []
+        self.nnz = []
+        self.h2d_bytes = 0
+        patterns = []
+        for k, m in enumerate(mats):
+            if m.shape != (self.n, self.n):
+                raise ValueError("all matrices must be n x n")
+            same = -1
+            for j, (pj, ptr_t, idx_t) in enumerate(patterns):
+                if pj.nnz == m.nnz and (pj.indptr is m.indptr or np.array_equal(pj.indptr, m.indptr)) and \
+                        (pj.indices is m.indices or np.array_equal(pj.indices, m.indices)):
+                    same = j
+                    break
+            if same >= 0:
+                ptr_t, idx_t = patterns[same][1], patterns[same][2]
+            else:
+                ptr_t, idx_t = to_device(m.indptr, torch), to_device(m.indices, torch)
+                self.h2d_bytes += m.indptr.nbytes + m.indices.nbytes
+            dat_t = to_device(m.data, torch)
+            self.h2d_bytes += m.data.nbytes
+            patterns.append((m, ptr_t, idx_t))
+            self._keep.append((ptr_t, idx_t, dat_t))
+            self.nnz.append(int(m.nnz))
+            check(lib().slmm_matset_bind_device(h, k, ptr_t.data_ptr(), idx_t.data_ptr(), dat_t.data_ptr(),
+                                                int(m.nnz), same))
+        self._out = torch.zeros(2 * self.K + 2 * self.K * self.K, dtype=torch.float64, device="cuda")
+
+    def values_ptr(self, k):
+        return self._keep[k][2].data_ptr()
+
+    def he_moments_device(self, y_dev, row_begin=0, row_end=None):
+        """Partial moments of rows [row_begin,row_end) as a device tensor (layout: include/scilmm_b200.h)."""
+        row_end = self.n if row_end is None else row_end
+        check(lib().slmm_he_moments(self._h, y_dev.data_ptr(), int(row_begin), int(row_end), self._out.data_ptr()))
+        return self._out
+
+    @staticmethod
+    def split_moments(out, K):
+        out = np.asarray(out)
+        q_off, q_diag = out[:K], out[K:2 * K]
+        S_off = out[2 * K:2 * K + K * K].reshape(K, K)
+        S_diag = out[2 * K + K * K:].reshape(K, K)
+        S_off = np.tril(S_off) + np.tril(S_off, -1).T
+        S_diag = np.tril(S_diag) + np.tril(S_diag, -1).T
+        return q_off, q_diag, S_off, S_diag
+
+    def spmm(self, k, X, out=None):
+        torch = _torch()
+        X2 = X if X.dim() == 2 else X.unsqueeze(1)
+        X2 = X2.contiguous()
+        ncols = X2.shape[1]
+        if out is None:
+            out = torch.empty_like(X2)
+        for c0 in range(0, ncols, 256):
+            c1 = min(ncols, c0 + 256)
+            if c0 == 0 and c1 == ncols:
+                check(lib().slmm_spmm(self._h, k, X2.data_ptr(), ncols, out.data_ptr()))
+            else:
+                blk = X2[:, c0:c1].contiguous()
+                o = torch.empty_like(blk)
+                check(lib().slmm_spmm(self._h, k, blk.data_ptr(), c1 - c0, o.data_ptr()))
+                out[:, c0:c1] = o
+        return out if X.dim() == 2 else out[:, 0]
+
+    def coldot(self, k, X, row_begin=0, row_end=None):
+        """d[c] = sum_i X[i,c] (A_k X)[i,c]  (device tensor of ncols doubles)."""
+        torch = _torch()
+        X2 = (X if X.dim() == 2 else X.unsqueeze(1)).contiguous()
+        ncols = X2.shape[1]
+        row_end = self.n if row_end is None else row_end
+        out = torch.empty(ncols, dtype=torch.float64, device="cuda")
+        for c0 in range(0, ncols, 256):
+            c1 = min(ncols, c0 + 256)
+            blk = X2 if (c0 == 0 and c1 == ncols) else X2[:, c0:c1].contiguous()
+            o = out if (c0 == 0 and c1 == ncols) else torch.empty(c1 - c0, dtype=torch.float64, device="cuda")
+            check(lib().slmm_spmm_coldot(self._h, k, blk.data_ptr(), c1 - c0, int(row_begin), int(row_end),
+                                         o.data_ptr()))
+            if o is not out:
+                out[c0:c1] = o
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().slmm_matset_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ factor
+class CholEngine(object):
+    """Symbolic analysis + device-resident supernodal factor (slmm_chol_t)."""
+
+    def __init__(self, pattern, ordering="metis", perm=None):
+        require_cuda()
+        pattern = canonical_csr(pattern)
+        self.n = pattern.shape[0]
+        h = C.c_void_p()
+        self._perm_in = None if perm is None else _as_i32(perm)
+        code = ORDERINGS[ordering] if perm is None else 1
+        check(lib().slmm_chol_analyze(self.n, np_ptr(pattern.indptr), np_ptr(pattern.indices), code,
+                                      None if perm is None else np_ptr(self._perm_in), C.byref(h)))
+        self._h = h
+        self._perm = None
+        self.factorizations = 0
+
+    def stats(self):
+        i = np.zeros(16, dtype=np.int64)
+        d = np.zeros(8, dtype=np.float64)
+        check(lib().slmm_chol_stats(self._h, np_ptr(i), np_ptr(d)))
+        return dict(n=int(i[0]), nsuper=int(i[1]), nlevels=int(i[2]), nnzL=int(i[3]), lsize=int(i[4]),
+                    exported_nnz=int(i[5]), max_front_rows=int(i[6]), max_super_cols=int(i[7]),
+                    ncomponents=int(i[8]), launches=int(i[9]), device_bytes=int(i[10]), flops=float(d[0]),
+                    t_order=float(d[1]), t_symbolic=float(d[2]), issued_flops=float(d[3]))
+
+    def perm(self):
+        if self._perm is None:
+            p = np.zeros(self.n, dtype=np.int32)
+            check(lib().slmm_chol_perm(self._h, np_ptr(p)))
+            self._perm = p
+        return self._perm
+
+    def register_pattern(self, pattern):
+        pattern = canonical_csr(pattern)
+        mid = C.c_int32(-1)
+        check(lib().slmm_chol_register_pattern(self._h, np_ptr(pattern.indptr), np_ptr(pattern.indices),
+                                               C.byref(mid)))
+        return mid.value
+
+    def add_values(self, map_id, values_ptr, sigma, first):
+        check(lib().slmm_chol_add_values(self._h, int(map_id), values_ptr, float(sigma), 1 if first else 0))
+
+    def factorize(self):
+        col = C.c_int32(-1)
+        code = lib().slmm_chol_factorize(self._h, C.byref(col))
+        check(code, col.value)
+        self.factorizations += 1
+
+    def logdet(self):
+        v = C.c_double(0.0)
+        check(lib().slmm_chol_logdet(self._h, C.byref(v)))
+        return v.value
+
+    def solve_(self, B, mode=0):
+        """In-place V^-1 B on a contiguous CUDA float64 tensor of shape (n,) or (n, k)."""
+        if not B.is_contiguous():
+            raise ValueError("solve_ needs a contiguous tensor")
+        nrhs = 1 if B.dim() == 1 else B.shape[1]
+        check(lib().slmm_chol_solve(self._h, B.data_ptr(), int(nrhs), int(mode)))
+        return B
+
+    def lmul(self, Z):
+        torch = _torch()
+        Z2 = (Z if Z.dim() == 2 else Z.unsqueeze(1)).contiguous()
+        out = torch.empty_like(Z2)
+        check(lib().slmm_chol_lmul(self._h, Z2.data_ptr(), out.data_ptr(), int(Z2.shape[1])))
+        return out if Z.dim() == 2 else out[:, 0]
+
+    def export_L(self):
+        st = self.stats()
+        nnz = st["exported_nnz"]
+        colptr = np.zeros(self.n + 1, dtype=np.int64)
+        rowidx = np.zeros(nnz, dtype=np.int32)
+        vals = np.zeros(nnz, dtype=np.float64)
+        check(lib().slmm_chol_export_L(self._h, np_ptr(colptr), np_ptr(rowidx), np_ptr(vals)))
+        return sp.csc_matrix((vals, rowidx, colptr), shape=(self.n, self.n))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().slmm_chol_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def gemm_selftest(M, N, K, lower=False, reps=5, seed=0):
+    """C = A B^T through the DMMA tile kernel; returns (max abs error vs torch fp64, ms, TFLOP/s)."""
+    torch = require_cuda()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(K, M, generator=g, dtype=torch.float64, device="cuda")   # column-major M x K
+    B = torch.randn(K, N, generator=g, dtype=torch.float64, device="cuda")   # column-major N x K
+    Cm = torch.zeros(N, M, dtype=torch.float64, device="cuda")               # column-major M x N
+    ms = C.c_float(0)
+    check(lib().slmm_gemm_selftest(M, N, K, A.data_ptr(), B.data_ptr(), Cm.data_ptr(), 1 if lower else 0, reps,
+                                   C.byref(ms)))
+    ref = (A.t() @ B).t()          # (N x M) row-major == column-major M x N
+    got = Cm
+    if lower:
+        mask = torch.tril(torch.ones(M, N, dtype=torch.bool, device="cuda")).t()
+        err = ((got - ref) * mask).abs().max().item()
+        flops = M * N * K
+    else:
+        err = (got - ref).abs().max().item()
+        flops = 2.0 * M * N * K
+    return err, ms.value, flops / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0

@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the golden vectors frozen
+from the unmodified reference.  Tolerances are the north-star ones: logdet / solves rel 1e-10, HE rel 1e-9,
+final variance components rel 1e-6, patterns / indexing bit-exact."""
+import numpy as np
+import pytest
+import scipy.linalg as la
+import scipy.sparse as sp
+
+from oracle import estimation as orc
+from oracle.cpu_factor import DenseFactor
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["golden_small", "golden_c1mini"]
+
+
+@pytest.fixture(scope="module")
+def slmm():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import scilmm_b200
+    from scilmm_b200 import SparseCholesky as SCmod  # noqa: F401
+    import sys
+    return sys.modules["scilmm_b200.SparseCholesky"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from scilmm_b200 import engine
+    return engine
+
+
+# ------------------------------------------------------------------------------------------ dense tiles
+@pytest.mark.parametrize("M,N,K,lower", [(64, 64, 64, False), (128, 128, 16, False), (200, 150, 37, False),
+                                         (513, 257, 130, False), (300, 300, 64, True), (1000, 40, 64, False),
+                                         (7, 5, 3, False), (140, 777, 64, False)])
+def test_dmma_gemm_tiles(eng, M, N, K, lower):
+    err, ms, tf = eng.gemm_selftest(M, N, K, lower=lower, reps=1)
+    assert err < 1e-11 * max(K, 1), (err, M, N, K)
+
+
+# ------------------------------------------------------------------------------------------ sparse kernels
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("tag", ["k1", "k3", "k4"])
+def test_he_moments_vs_oracle(case, tag, request, slmm):
+    g = request.getfixturevalue(case)
+    mats = g.mats(tag)
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(g.n)
+    for mqs in (False, True):
+        q, S, _ = slmm.he_moments(mats, y, MQS=mqs)
+        qo, So = orc.he_moments(mats, y, MQS=mqs)
+        assert rel_err(q, qo) < 1e-11
+        assert rel_err(S, So) < 1e-11
+
+
+def test_he_moments_row_shards_add_up(golden_c1mini, eng):
+    import torch
+    g = golden_c1mini
+    ms = eng.MatSet(g.mats("k3"))
+    y = eng.to_device(np.random.default_rng(2).standard_normal(g.n))
+    full = ms.he_moments_device(y).clone()
+    cut = g.n // 3
+    a = ms.he_moments_device(y, 0, cut).clone()
+    b = ms.he_moments_device(y, cut, g.n).clone()
+    empty = ms.he_moments_device(y, cut, cut).clone()
+    assert torch.all(empty == 0)
+    assert rel_err((a + b).cpu().numpy(), full.cpu().numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_he_estimates_vs_golden(case, request, slmm):
+    g = request.getfixturevalue(case)
+    for tag in ("k1", "k3"):
+        est = slmm.HE(g.mats(tag), g["cov"], g["y"].copy(), compute_stderr=False)
+        assert rel_err(est, g["he_" + tag]) < 1e-9
+        est = slmm.HE(g.mats(tag), g["cov"], g["y"].copy(), MQS=True, compute_stderr=False)
+        assert rel_err(est, g["he_mqs_" + tag]) < 1e-9
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_he_stderr_and_bivariate_vs_golden(case, request, slmm):
+    g = request.getfixturevalue(case)
+    for tag in ("k1", "k3"):
+        np.random.seed(g.seed + 2)
+        est, se = slmm.HE(g.mats(tag), g["cov"], g["y"].copy(), compute_stderr=True, sim_num=g.sim_num)
+        assert rel_err(est, g["he_" + tag]) < 1e-9
+        assert np.allclose(se, g["he_se_" + tag], rtol=1e-8, equal_nan=True)
+    np.random.seed(g.seed + 3)
+    mats = g.mats("k1")
+    y2 = g["y2"].copy()
+    est, se = slmm.HE(mats, g["cov"], g["y"].copy(), compute_stderr=True, sim_num=g.sim_num, y2=y2)
+    assert rel_err(est, g["he_biv"]) < 1e-9
+    assert np.allclose(se, g["he_biv_se"], rtol=1e-8, equal_nan=True)
+    assert mats[0].shape == (2 * g.n, 2 * g.n)          # reference mutates mat_list in place (:211)
+
+
+def test_spmm_and_coldot(golden_c1mini, eng):
+    g = golden_c1mini
+    mats = g.mats("k3")
+    ms = eng.MatSet(mats)
+    rng = np.random.default_rng(4)
+    for ncols in (1, 3, 33, 101, 128, 140):
+        X = rng.standard_normal((g.n, ncols))
+        Xd = eng.to_device(X)
+        for k in (0, 2):
+            ref = mats[k].dot(X)
+            assert rel_err(ms.spmm(k, Xd).cpu().numpy(), ref) < 1e-13
+            assert rel_err(ms.coldot(k, Xd).cpu().numpy(), np.sum(ref * X, axis=0)) < 1e-12
+    x1 = rng.standard_normal(g.n)
+    assert rel_err(ms.spmm(1, eng.to_device(x1)).cpu().numpy(), mats[1].dot(x1)) < 1e-13
+
+
+# ------------------------------------------------------------------------------------------ factorization
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("tag", ["k2", "k4"])
+@pytest.mark.parametrize("ordering", ["natural", "nesdis"])
+def test_factor_protocol_vs_golden(case, tag, ordering, request, slmm):
+    g = request.getfixturevalue(case)
+    V = g.csc("V_" + tag)
+    chol = slmm.SparseCholesky(ordering_method=ordering)
+    f = chol(V)
+    assert abs(f.logdet() - g["logdet_" + tag]) < 1e-10 * abs(g["logdet_" + tag])
+    ys = g["y"] / g["y"].std()
+    assert rel_err(f(ys), g["Viy_" + tag]) < 1e-10
+    assert rel_err(f(g["cov"]), g["ViC_" + tag]) < 1e-10
+    P = f.P()
+    assert P.dtype == np.int32 and sorted(P.tolist()) == list(range(g.n))
+    L = f.L()
+    assert sp.isspmatrix_csc(L) and sp.triu(L, 1).nnz == 0
+    Vp = V.toarray()[P][:, P]
+    assert np.max(np.abs((L @ L.T).toarray() - Vp)) < 1e-12 * np.max(np.abs(Vp))
+    if ordering == "natural":
+        assert np.array_equal(P, np.arange(g.n))
+        ref = DenseFactor(V)
+        assert rel_err(L.toarray(), ref.L().toarray()) < 1e-11
+    # second factorization with the same pattern reuses the analysis and invalidates the old Factor
+    f2 = chol(V * 2.0)
+    assert abs(f2.logdet() - (g["logdet_" + tag] + g.n * np.log(2.0))) < 1e-10 * abs(g["logdet_" + tag])
+    with pytest.raises(RuntimeError):
+        f.logdet()
+    assert len(chol._engines) == 1
+
+
+def test_lmul_and_probe_vectors(golden_c1mini, slmm, eng):
+    g = golden_c1mini
+    V = g.csc("V_k4")
+    for ordering in ("natural", "nesdis"):
+        f = slmm.SparseCholesky(ordering_method=ordering)(V)
+        P = f.P()
+        ref = DenseFactor(V, P)
+        rng = np.random.default_rng(7)
+        Z = rng.standard_normal((g.n, 37))
+        got = f.lmul(eng.to_device(Z)).cpu().numpy()
+        want = ref.L().dot(Z)[np.argsort(P)]
+        assert rel_err(got, want) < 1e-11
+        np.random.seed(3)
+        W = slmm.simulate_vector(f, g.n, 20, None)
+        np.random.seed(3)
+        Wo = orc.probe_vectors(ref, np.random.randn(g.n, 20), np.argsort(P))
+        assert rel_err(W, Wo) < 1e-10
+
+
+def test_not_positive_definite_raises(golden_small, slmm):
+    V = golden_small.csc("V_k2").tolil()
+    V[5, 5] = -3.0
+    with pytest.raises(slmm.NotPositiveDefiniteError):
+        slmm.SparseCholesky()(V.tocsc())
+
+
+def test_wide_supernodes_and_many_rhs(slmm, eng):
+    # one dense 300 x 300 block (several 64-wide diagonal blocks, outer block boundary at 256) + a sparse tail
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((300, 300))
+    D = B @ B.T + 300 * np.eye(300)
+    T = sp.random(500, 500, 0.01, random_state=3)
+    T = T + T.T + 30 * sp.eye(500)
+    V = sp.block_diag([D, T]).tolil()
+    V[300:320, 0:40] = 0.5
+    V[0:40, 300:320] = 0.5
+    V = V.tocsc()
+    for ordering in ("natural", "nesdis"):
+        f = slmm.SparseCholesky(ordering_method=ordering)(V)
+        sign, ld = np.linalg.slogdet(V.toarray())
+        assert abs(f.logdet() - ld) < 1e-10 * abs(ld)
+        Bm = rng.standard_normal((800, 150))
+        X = f(Bm)
+        assert rel_err(V @ X, Bm) < 1e-10
+        assert rel_err(X, np.linalg.solve(V.toarray(), Bm)) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------ REML
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("tag", ["k2", "k4"])
+def test_reml_evaluation_vs_golden(case, tag, request, slmm):
+    g = request.getfixturevalue(case)
+    mats, sig = g.mats(tag), g["sig_" + tag]
+    ys = g["y"] / g["y"].std()
+    chol = slmm.SparseCholesky(ordering_method="natural")      # golden vectors were frozen with P = identity
+    for reml in (False, True):
+        np.random.seed(g.seed + 4)
+        nll, grad = slmm.bolt_gradient_estimation(np.log(sig), chol, mats, g["cov"], ys, reml, g.sim_num, False)
+        assert abs(nll - g["bolt_nll_%s_%d" % (tag, reml)]) < 1e-10 * abs(nll)
+        assert rel_err(grad, g["bolt_grad_%s_%d" % (tag, reml)]) < 1e-8
+    f = chol._session(mats, g["cov"], ys).factor_at(sig)
+    H = slmm.compute_hess(mats, g["cov"], f, ys)
+    assert rel_err(H, g["hess_" + tag]) < 1e-9
+    assert rel_err(slmm.compute_varcomp_stderr(mats, g["cov"], f, ys, g.sim_num), g["se_" + tag]) < 1e-9
+
+
+def test_reml_evaluation_shared_permutation_vs_oracle(golden_c1mini, slmm):
+    # engine's own nested-dissection P, oracle forced onto the same P and the same Z stream
+    g = golden_c1mini
+    mats, sig = g.mats("k4"), g["sig_k4"]
+    ys = g["y"] / g["y"].std()
+    chol = slmm.SparseCholesky()
+    np.random.seed(99)
+    nll, grad = slmm.bolt_gradient_estimation(np.log(sig), chol, mats, g["cov"], ys, True, 50, False)
+    P = chol._session(mats, g["cov"], ys).eng.perm()
+    np.random.seed(99)
+    nll_o, grad_o = orc.reml_evaluation(np.log(sig), lambda M: DenseFactor(M, P), mats, g["cov"], ys, True, 50)
+    assert abs(nll - nll_o) < 1e-10 * abs(nll_o)
+    assert rel_err(grad, grad_o) < 1e-8
+
+
+@pytest.mark.parametrize("tag,base", [("k2", "k1"), ("k4", "k3")])
+def test_full_reml_fit_vs_golden(tag, base, golden_small, slmm):
+    g = golden_small
+    np.random.seed(g.seed + 5)
+    out = slmm.REML(slmm.SparseCholesky(ordering_method="natural"), g.mats(base), g["cov"], g["y"].copy(),
+                    reml=True, sim_num=g.sim_num)
+    assert rel_err(out["covariance coefficients"], g["reml_sig_" + tag]) < 1e-6
+    assert rel_err(out["covariates coefficients"], g["reml_beta_" + tag]) < 1e-6
+    assert rel_err(out["covariance std"], g["reml_se_" + tag]) < 1e-6
+    assert set(["covariance coefficients", "covariates coefficients", "covariance std"]) <= set(out)
+    assert np.isfinite(out["nll"])
+
+
+def test_run_estimates_dropin(golden_c1mini, slmm):
+    import pandas as pd
+    g = golden_c1mini
+    A = g.csr("A")
+    n = g.n
+    cov = pd.DataFrame({"c0": g["cov"][:, 0], "c1": g["cov"][:, 1]})
+    phe = pd.Series(g["y"])
+    np.random.seed(5)
+    est, se = slmm.run_estimates(A, phe, cov, reml=False, ignore_indices=True)
+    covm = np.hstack([g["cov"][:, :2], np.ones((n, 1))])
+    covm[:, :-1] -= covm[:, :-1].mean(axis=0)
+    covm[:, :-1] /= covm[:, :-1].std(axis=0)
+    np.random.seed(5)
+    est_o, se_o = orc.he_regression([A], covm, g["y"].copy(), compute_stderr=True)
+    assert rel_err(est, est_o) < 1e-9 and rel_err(se, se_o) < 1e-7

@@ -1,0 +1,130 @@
+"""Host logic (no GPU): symbolic analysis checked by emulating the multifrontal plan in numpy, and the
+C-ABI surface (every symbol declared in include/scilmm_b200.h is exported by the library)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.linalg as la
+import scipy.sparse as sp
+
+from scilmm_b200 import _lib
+from scilmm_b200.engine import SymbolicView
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def emulate_plan(V, sym):
+    """Run the engine's plan (entry map -> parent-pull extend-add -> partial dense Cholesky per front, levels
+    deepest first) with numpy; returns the dense permuted factor."""
+    a = sym.arrays()
+    n = sym.n
+    Vc = sp.csr_matrix(V)
+    Vc.sort_indices()
+    Lx = np.zeros(sym.lsize)
+    tgt = sym.entry_map(Vc)
+    ok = tgt >= 0
+    assert ok.sum() == (Vc.nnz + n) // 2            # one copy of every symmetric pair + the diagonal
+    np.add.at(Lx, tgt[ok], Vc.data[ok])
+    children = [[] for _ in range(sym.nsuper)]
+    for s in range(sym.nsuper):
+        if a['sn_parent'][s] >= 0:
+            children[a['sn_parent'][s]].append(s)
+    U = {}
+    L = np.zeros((n, n))
+    for lev in range(sym.nlevels - 1, -1, -1):
+        for s in a['level_sn'][a['level_ptr'][lev]:a['level_ptr'][lev + 1]]:
+            f = a['sn_first'][s]
+            ns = a['sn_first'][s + 1] - f
+            ms = a['sn_nrow'][s]
+            rs = ms - ns
+            rows = a['rows'][a['sn_rowptr'][s]:a['sn_rowptr'][s + 1]]
+            assert np.array_equal(rows[:ns], np.arange(f, f + ns)) and np.all(np.diff(rows) > 0)
+            P = Lx[a['sn_lptr'][s]:a['sn_lptr'][s + 1]].reshape(ns, ms).T.copy()
+            F22 = np.zeros((rs, rs))
+            for c in children[s]:
+                nsc = a['sn_first'][c + 1] - a['sn_first'][c]
+                relc = a['rel'][a['sn_rowptr'][c] + nsc:a['sn_rowptr'][c + 1]]
+                Uc = U.pop(c)
+                for tt in range(relc.size):
+                    for u in range(tt, relc.size):
+                        if relc[tt] < ns:
+                            P[relc[u], relc[tt]] += Uc[u, tt]
+                        else:
+                            F22[relc[u] - ns, relc[tt] - ns] += Uc[u, tt]
+            D = np.tril(P[:ns, :ns])
+            D = D + np.tril(D, -1).T
+            L11 = la.cholesky(D, lower=True)
+            L21 = la.solve_triangular(L11, P[ns:, :].T, lower=True).T if rs else np.zeros((0, ns))
+            U[s] = (np.tril(F22) + np.tril(F22, -1).T - L21 @ L21.T) if rs else np.zeros((0, 0))
+            L[np.ix_(rows[:ns], np.arange(f, f + ns))] = L11
+            if rs:
+                L[np.ix_(rows[ns:], np.arange(f, f + ns))] = L21
+    return L, a
+
+
+@pytest.mark.parametrize("ordering", ["natural", "metis"])
+@pytest.mark.parametrize("tag", ["k2", "k4"])
+def test_plan_reproduces_dense_cholesky(golden_small, ordering, tag):
+    V = golden_small.csc("V_" + tag)
+    sym = SymbolicView(V, ordering=ordering)
+    L, a = emulate_plan(V, sym)
+    perm = a['perm']
+    assert sorted(perm.tolist()) == list(range(sym.n))
+    if ordering == "natural":
+        assert np.array_equal(perm, np.arange(sym.n))
+    Lref = la.cholesky(V.toarray()[perm][:, perm], lower=True)
+    assert np.max(np.abs(L - Lref)) < 1e-12
+    true_counts = (np.abs(Lref) > 0).sum(axis=0)
+    assert np.array_equal(true_counts, a['colcount'])
+    assert sym.nnzL == true_counts.sum()
+    assert sym.flops == float((true_counts.astype(float) ** 2).sum())
+
+
+def test_given_permutation_is_kept(golden_small):
+    V = golden_small.csc("V_k2")
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(golden_small.n).astype(np.int32)
+    sym = SymbolicView(V, perm=perm)
+    L, a = emulate_plan(V, sym)
+    assert np.array_equal(a['perm'], perm)
+    Lref = la.cholesky(V.toarray()[perm][:, perm], lower=True)
+    assert np.max(np.abs(L - Lref)) < 1e-12
+
+
+def test_edge_patterns():
+    # diagonal matrix, one dense block, and a ragged mix with isolated vertices
+    for M in (sp.eye(7).tocsr(), sp.csr_matrix(np.ones((9, 9)) + 9 * np.eye(9)),
+              sp.block_diag([np.ones((5, 5)) + 5 * np.eye(5), np.eye(3), [[4.0, 1], [1, 4]]]).tocsr()):
+        for ordering in ("natural", "metis"):
+            sym = SymbolicView(M, ordering=ordering)
+            L, a = emulate_plan(M, sym)
+            p = a['perm']
+            assert np.max(np.abs(L @ L.T - M.toarray()[p][:, p])) < 1e-12
+
+
+def test_c1mini_sizes(golden_c1mini):
+    V = golden_c1mini.csc("V_k4")
+    sym = SymbolicView(V, ordering="metis")
+    assert sym.nsuper < sym.n and sym.nlevels < 64
+    assert sym.lsize >= sym.nnzL
+    a = sym.arrays()
+    # levels partition the supernodes and every child sits exactly one level below its parent
+    depth = np.full(sym.nsuper, -1)
+    for lev in range(sym.nlevels):
+        depth[a['level_sn'][a['level_ptr'][lev]:a['level_ptr'][lev + 1]]] = lev
+    assert np.all(depth >= 0)
+    has_parent = a['sn_parent'] >= 0
+    assert np.all(depth[has_parent] == depth[a['sn_parent'][has_parent]] + 1)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "scilmm_b200.h")).read()
+    declared = set(re.findall(r"\b(slmm_[a-z_A-Z0-9]+)\s*\(", header))
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (slmm_\w+)", out))
+    assert declared, "no declarations parsed"
+    assert declared <= exported, "missing: %s" % sorted(declared - exported)
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.lib().slmm_version() == 100
