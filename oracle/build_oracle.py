@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY - compiles oracle/cpu_kernels.c into oracle/_build/liboracle_cpu.so (gcc, OpenMP)."""
+"""TEST INFRASTRUCTURE ONLY - compiles oracle/cpu_kernels.c into oracle/_build/liboracle_cpu.so (gcc)."""
 import os
 import subprocess
 
@@ -12,7 +12,7 @@ def build(force=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    subprocess.check_call(["gcc", "-O3", "-fopenmp", "-shared", "-fPIC", src, "-o", LIB])
+    subprocess.check_call(["gcc", "-O3", "-shared", "-fPIC", src, "-o", LIB])
     return LIB
 
 
