@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the SparseCholesky path on B200 (contract: one JSON line on rank 0).
+
+Workload (BASELINE.json config 3): simulated pedigree of 250,000 individuals (sparsity_factor 1e-3,
+gen_exp 1.4, init_keep_rate 0.8, seed 0) -> IBD A, epistasis A o A, identity; 10 covariates + intercept;
+one "step" = one REML evaluation (`bolt_gradient_estimation`, reference scilmm/SparseCholesky.py:77-117):
+V assembly, supernodal LL' factorization, logdet, c+1 deterministic solve columns, 128 Hutchinson probe
+columns through L*Z + solve, fused SpMM quadratic forms, REML trace correction.  Symbolic analysis happens
+once before the loop and is reported separately.  A Haseman-Elston fit (BASELINE.json config 4, K=3) is
+timed as a secondary result in the same line (`he`).
+
+  value      seconds per REML evaluation with every input resident in HBM (probes drawn on the device)
+  e2e        the same evaluation through the public API with host buffers: host sigma + host probe block
+             (pinned) copied in, nll + gradient copied out, every step
+  roofline   the dominant kernel (FP64 DMMA tile GEMM): issued dense flops / device time of its launches,
+             measured with CUDA events on the launching stream in a separate profiled pass
+  cpu_baseline  the oracle port (oracle/estimation.py + oracle/supernodal_cpu.py) on the host cores
+
+Multi-GPU (torchrun): factor replicated, probe columns sharded, one NCCL allreduce of K doubles per
+evaluation ("strong" scaling: total work fixed).  --impl reference runs the oracle CPU arm only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# removal fractions found once by simulate_pedigree's bisection (seed 0); avoids repeating the search
+REMOVE_FRAC = {(250000, 1e-3): 0.065625, (100000, 1e-3): 0.084375, (20000, 1e-3): None,
+               (1000000, 1e-4): 0.103125}
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def make_inputs(n, sf, ncov, seed=0, with_household=False):
+    from scilmm_b200 import pedigree as P
+    t0 = time.time()
+    ped = P.simulate_pedigree(n, sf, seed=seed, remove_frac=REMOVE_FRAC.get((n, sf)))
+    A, T, D, F = P.numerator(ped["rel"])
+    extra = []
+    if with_household:
+        extra.append(P.household_matrix(ped["household"]))
+    keep, out = P.drop_unrelated(A, *extra)
+    A = out[0]
+    nn = A.shape[0]
+    rng = np.random.default_rng(seed + 1)
+    cov = rng.standard_normal((nn, ncov))
+    y = P.quick_phenotype(T, D, np.zeros((n, 0)), 0.4, np.zeros(0), rng)[keep]
+    cov = np.hstack([cov, np.ones((nn, 1))])
+    cov[:, :-1] -= cov[:, :-1].mean(axis=0)
+    cov[:, :-1] /= cov[:, :-1].std(axis=0)
+    y = y + cov[:, :-1].dot(np.full(ncov, 0.05))
+    info = dict(n_sim=n, n=nn, nnz=int(A.nnz), sf=sf, seed=seed, remove_frac=ped["remove_frac"],
+                gen_s=round(time.time() - t0, 1))
+    return A, (out[1] if with_household else None), cov, y, info
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reml_sample(mats, cov, y, sig, reml, sim_num, sample_cols):
+    """Oracle REML evaluation on the host: full assembly + factorization + logdet + deterministic solves; the
+    probe pipeline (L*Z, solve, SpMM reductions) on `sample_cols` columns, scaled to sim_num columns."""
+    from oracle import estimation as orc
+    from oracle.supernodal_cpu import SupernodalCPUFactor, SupernodalPlan
+    import scipy.linalg as la
+    t = {}
+    t0 = time.time()
+    V = orc.weighted_sum(mats, sig)
+    t["assemble"] = time.time() - t0
+    t0 = time.time()
+    plan = SupernodalPlan(sp.csr_matrix((V.data, V.indices, V.indptr), shape=V.shape))
+    t["analyze"] = time.time() - t0           # the reference repays this on every evaluation (:22-26 from :92)
+    t0 = time.time()
+    f = SupernodalCPUFactor(V, plan=plan)
+    logdet = f.logdet()
+    t["factor"] = time.time() - t0
+    t0 = time.time()
+    ViC, chol, mu, beta = orc.fixed_effects(f, y, cov)
+    Vir = f(y - mu)
+    nll = orc.nll_value(f, y, Vir, mu, chol, reml)
+    t["fixed"] = time.time() - t0
+    t0 = time.time()
+    rng = np.random.default_rng(7)
+    Z = rng.standard_normal((y.size, sample_cols))
+    W = f(f.lmul_unperm(Z))
+    for k in range(len(mats)):
+        _ = np.sum(mats[k].dot(W) * W, axis=0)
+    t["probe_sample"] = time.time() - t0
+    t0 = time.time()
+    for k in range(len(mats)):
+        _ = Vir.dot(mats[k].dot(Vir))
+        if reml:
+            _ = la.cho_solve(chol, ViC.T.dot(mats[k].dot(ViC)))
+    t["quad"] = time.time() - t0
+    scale = float(sim_num) / sample_cols
+    total_cached = t["assemble"] + t["factor"] + t["fixed"] + t["quad"] + scale * t["probe_sample"]
+    return dict(seconds=total_cached, seconds_with_reanalysis=total_cached + t["analyze"], parts=t, nll=nll,
+                logdet=logdet, flops=plan.sym.flops)
+
+
+def cpu_he(mats, cov, y):
+    from oracle import estimation as orc
+    t0 = time.time()
+    est = orc.he_regression(list(mats), cov, y.copy(), compute_stderr=False)
+    return time.time() - t0, est
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=250000)
+    ap.add_argument("--sf", type=float, default=1e-3)
+    ap.add_argument("--probes", type=int, default=128)
+    ap.add_argument("--ncov", type=int, default=10)
+    ap.add_argument("--he-n", type=int, default=1000000)
+    ap.add_argument("--he-sf", type=float, default=1e-4)
+    ap.add_argument("--skip-he", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-cols", type=int, default=8)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sig = np.array([0.3, 0.15, 0.55])
+    workload = "REML evaluation, simulated pedigree %d (sf=%g), K=3 (IBD, AoA, I), c=%d+1, %d probes" % (
+        args.n, args.sf, args.ncov, args.probes)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        A, _, cov, y, info = make_inputs(args.n, args.sf, args.ncov)
+        from scilmm_b200 import pedigree as P
+        mats = [A, P.epistasis(A), sp.eye(A.shape[0]).tocsr()]
+        ys = y / y.std()
+        vals = []
+        for i in range(args.warmup + args.steps):
+            if i < args.warmup and i > 0:
+                continue                      # one warm-up pass is enough on the CPU (no clocks / caches to settle)
+            r = cpu_reml_sample(mats, cov, ys, sig, True, args.probes, args.cpu_cols)
+            log("reference step", i, r["parts"], "->", round(r["seconds_with_reanalysis"], 2), "s")
+            if i >= args.warmup:
+                vals.append(r["seconds_with_reanalysis"])
+        v = float(np.mean(vals))
+        sample = ("oracle port: full assembly + METIS analysis + supernodal LAPACK factorization + logdet + "
+                  "deterministic solves; probe pipeline on %d of %d columns scaled x%g; analysis repeated per "
+                  "evaluation as the reference does" % (args.cpu_cols, args.probes, args.probes / args.cpu_cols))
+        print(json.dumps({"impl": "reference", "metric": "reml_iter_time", "value": v, "unit": "s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": workload, **info},
+                          "cpu_baseline": {"value": v, "unit": "s", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": sample},
+                          "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from scilmm_b200 import engine as E
+    from scilmm_b200 import pedigree as P
+    import scilmm_b200.SparseCholesky  # noqa: F401
+    S = sys.modules["scilmm_b200.SparseCholesky"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    A, _, cov, y, info = make_inputs(args.n, args.sf, args.ncov)
+    log("inputs", info)
+    n = A.shape[0]
+    mats = [A, P.epistasis(A), sp.eye(n).tocsr()]
+    ys = y / y.std()
+    K = len(mats)
+    s = args.probes
+
+    chol = S.SparseCholesky(rng="device")
+    t0 = time.time()
+    ses = chol._session(mats, cov, ys)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    st = ses.eng.stats()
+    log("session %.1fs" % setup_s, {k: st[k] for k in ("nsuper", "nlevels", "nnzL", "lsize", "flops",
+                                                       "max_front_rows", "launches", "device_bytes")})
+
+    # ---------------- device-resident steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()                       # started before the warm-up so its start-up cost stays outside the timed region
+    for _ in range(args.warmup):
+        ses.evaluate(sig, True, s)
+    barrier()
+    sampler.lines = []
+    E.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        nll, grad = ses.evaluate(sig, True, s)
+    e1.record()
+    barrier()
+    launches = E.launch_count()
+    clocks = sampler.stop()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    # factorization alone (Cholesky GFLOP/s of the metric) and solve / reduction phases
+    def ev(fn, reps=2):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    def assemble():
+        for k in range(K):
+            ses.eng.add_values(ses.map_ids[k], ses.matset.values_ptr(k), float(sig[k]), k == 0)
+
+    def assemble_factor():
+        assemble()
+        ses.eng.factorize()
+
+    t_asm = ev(assemble)
+    t_fac = ev(assemble_factor) - t_asm
+    Bs = torch.randn(n, s, dtype=torch.float64, device="cuda")
+    t_solve = ev(lambda: ses.eng.solve_(Bs.clone())) - ev(lambda: Bs.clone())
+    t_lmul = ev(lambda: ses.eng.lmul(Bs))
+    Xq = torch.randn(n, s + 1, dtype=torch.float64, device="cuda")
+    t_quad = ev(lambda: [ses.matset.coldot(k, Xq) for k in range(K)])
+    # profiled pass: per-kernel-kind device time with events around every launch
+    assemble()
+    ses.eng.set_profiling(True)
+    ses.eng.factorize()
+    prof = ses.eng.profile()
+    ses.eng.set_profiling(False)
+    gb = prof["gemm_big"]
+    # FP64 tensor peak: cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+    Mg = 8192
+    ga = torch.randn(Mg, Mg, dtype=torch.float64, device="cuda")
+    gbm = torch.randn(Mg, Mg, dtype=torch.float64, device="cuda")
+    t_dgemm = ev(lambda: torch.matmul(ga, gbm), reps=3)
+    dgemm_tflops = 2.0 * Mg ** 3 / t_dgemm / 1e9
+    del ga, gbm
+    achieved = gb["flops"] / gb["ms"] / 1e9 if gb["ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tiles_kernel<128,128> (FP64 DMMA)", "achieved": round(achieved, 3),
+                "peak": round(dgemm_tflops, 3), "unit": "TFLOP/s", "frac": round(achieved / dgemm_tflops, 4),
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "traffic": None, "launches": gb["launches"], "kernel_ms_per_factorization": round(gb["ms"], 2),
+                "share_of_factorization": round(gb["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())), 3)}
+    peaks = measured_peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+    nnzs = ses.matset.nnz
+    solve_bytes = 2.0 * (8.0 * st["lsize"]) + 2 * 2 * 8.0 * n * s
+    quad_bytes = sum(12.0 * z + 4 * (n + 1) for z in nnzs[:1]) + 8.0 * nnzs[1] + 12.0 * nnzs[2] + K * 8.0 * n * (s + 1)
+    phases = {
+        "assemble_ms": round(t_asm, 3), "factorize_ms": round(t_fac, 2), "solve128_ms": round(t_solve, 2),
+        "lmul128_ms": round(t_lmul, 2), "quadforms_ms": round(t_quad, 2),
+        "cholesky_gflops": round(st["flops"] / t_fac / 1e6, 1),
+        "cholesky_issued_gflops": round(st["issued_flops"] / t_fac / 1e6, 1),
+        "solve_gbs": round(solve_bytes / t_solve / 1e6, 1), "quadforms_gbs": round(quad_bytes / t_quad / 1e6, 1),
+        "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src,
+        "profile_ms": {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]},
+    }
+
+    # ---------------- e2e through the public API with host buffers
+    chol_h = S.SparseCholesky(rng="host_buffer")
+    chol_h._engines = chol._engines                      # same analysis; the session re-registers patterns
+    Zhost = torch.from_numpy(np.random.default_rng(5).standard_normal((n, s))).pin_memory()
+    chol_h.probe_source = lambda nn, ss: Zhost
+    log_sig = np.log(sig)
+    for _ in range(2):
+        S.bolt_gradient_estimation(log_sig, chol_h, mats, cov, ys, True, s, False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nll_h, grad_h = S.bolt_gradient_estimation(log_sig, chol_h, mats, cov, ys, True, s, False)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e = {"value": round(e2e_s, 4), "unit": "s", "h2d_bytes_per_step": int(Zhost.numel() * 8 + K * 8),
+           "d2h_bytes_per_step": int((K + 1) * 8 + (K * (cov.shape[1] ** 2 + 2) + 2 * cov.shape[1] ** 2) * 8),
+           "api": "scilmm_b200.bolt_gradient_estimation(log_sig, SparseCholesky(), mats, cov, y, True, 128, False)"}
+
+    # ---------------- HE (config 4) secondary result
+    he = None
+    if not args.skip_he and world == 1:
+        try:
+            he = bench_he(args, E, P, S, torch, hbm)
+        except Exception as ex:   # keep the headline line even if the secondary workload cannot be generated
+            he = {"error": repr(ex)}
+
+    # ---------------- CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        r = cpu_reml_sample(mats, cov, ys, sig, True, s, args.cpu_cols)
+        log("cpu parts", r["parts"])
+        cpu = {"value": round(r["seconds_with_reanalysis"], 2), "unit": "s", "cores": os.cpu_count(), "kind": "port",
+               "value_analysis_cached": round(r["seconds"], 2),
+               "parts_s": {k: round(v, 2) for k, v in r["parts"].items()},
+               "cholesky_gflops": round(r["flops"] / r["parts"]["factor"] / 1e9, 1),
+               "nll_rel_diff_vs_gpu": abs(r["nll"] - nll_h) / abs(r["nll"]),
+               "sample": "oracle port (CHOLMOD is not installed): full assembly, METIS analysis, supernodal LAPACK "
+                         "factorization on all cores, logdet, deterministic solves; probe pipeline on %d of %d "
+                         "columns scaled x%g; value includes the per-evaluation re-analysis the reference performs"
+                         % (args.cpu_cols, s, s / args.cpu_cols)}
+
+    if rank == 0:
+        out = {"metric": "reml_iter_time", "value": round(step_ms / 1e3, 5), "unit": "s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 3),
+               "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": workload, "l2": "inputs larger than L2 (factor panels %.1f GB)" %
+                          (st["lsize"] * 8 / 1e9), **info, "nnzL": st["nnzL"], "factor_flops": st["flops"],
+                          "nsuper": st["nsuper"], "levels": st["nlevels"], "max_front": st["max_front_rows"],
+                          "symbolic_s": round(st["t_order"] + st["t_symbolic"], 2), "session_setup_s": round(setup_s, 1),
+                          "parallelism": "probe columns sharded x%d, factor replicated" % world},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+               "phases": phases, "cpu_baseline": cpu, "he": he,
+               "nll": float(nll), "grad": [float(g) for g in grad]}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_he(args, E, P, S, torch, hbm):
+    """Haseman-Elston fit, K=3 (IBD, AoA, household), BASELINE config 4."""
+    A, H, cov, y, info = make_inputs(args.he_n, args.he_sf, 2, seed=0, with_household=True)
+    n = A.shape[0]
+    mats = [A, P.epistasis(A), H]
+    log("HE inputs", info, "nnz(H)", H.nnz)
+    ms = E.MatSet(mats)
+    yd = E.to_device(y)
+
+    def run():
+        return ms.he_moments_device(yd)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / reps
+    alg_bytes = (12.0 * A.nnz + 4 * (n + 1)) + 8.0 * A.nnz + (12.0 * H.nnz + 4 * (n + 1)) + 3 * 8.0 * n
+    t0 = time.perf_counter()
+    est = S.HE(list(mats), cov, y.copy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    out = {"workload": "HE fit, simulated pedigree %d (sf=%g), K=3 (IBD, AoA, household)" % (args.he_n, args.he_sf),
+           **info, "nnz_household": int(H.nnz), "device_ms": round(dev_ms, 4), "e2e_s": round(e2e_s, 3),
+           "h2d_bytes": int(ms.h2d_bytes + 8 * n), "estimates": [float(v) for v in est],
+           "roofline": {"bound": "hbm", "kernel": "he_group_kernel<2> + he_group_kernel<1> + he_cross_kernel x2",
+                        "achieved": round(alg_bytes / dev_ms / 1e6, 1), "peak": hbm, "unit": "GB/s",
+                        "frac": round(alg_bytes / dev_ms / 1e6 / hbm, 4), "algorithmic_bytes": alg_bytes}}
+    if not args.skip_cpu:
+        t_cpu, est_cpu = cpu_he(mats, cov, y)
+        out["cpu_baseline"] = {"value": round(t_cpu, 2), "unit": "s", "cores": 1, "kind": "port",
+                               "sample": "full oracle HE fit (scipy single-threaded kernels, as the reference)",
+                               "rel_diff_vs_gpu": float(np.max(np.abs(est - est_cpu)) / np.max(np.abs(est_cpu)))}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,14 @@ int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrh
 /* factor.L() as host CSC (colptr int64[n+1], rowidx int32[nnz], values double[nnz]; nnz = stats i[5]) */
 int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, double* h_values);
 
+/* Instrumentation.  slmm_launch_count: kernels launched by this library since the last reset.
+ * Profiling mode brackets every launch of the factor / solve schedules with CUDA events on the launching stream and
+ * sums the time per kernel kind: 0 potrf+inverse, 1 DMMA GEMM 128x128 tiles, 2 DMMA GEMM 64x64 tiles,
+ * 3 extend-add, 4 RHS pull, 5 unused.  flops6 = dense flops issued per kind. */
+int slmm_launch_count(int64_t* out, int32_t reset);
+int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on);
+int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6);
+
 /* Host-only view of the symbolic analysis (no CUDA device needed): used by the host-logic tests and to size a
  * problem before touching the GPU.  i_out as slmm_chol_stats i[0..8] plus i[9]=total rows entries; the array
  * getters may be NULL. */

@@ -23,6 +23,22 @@ import scipy.sparse as sp
 from oracle import build_oracle
 
 _lib = None
+_threads = {"cur": None, "max": None}
+SMALL_WORK = 200000      # ms * ns below which BLAS runs single-threaded (thread fork/join costs more than the op)
+
+
+def _set_blas_threads(big):
+    """OpenBLAS wakes every thread even for tiny operands; tens of thousands of small fronts then cost ~1 ms
+    each.  Small fronts run on one thread, large fronts on all host cores (what a tuned CHOLMOD build does
+    through its BLAS)."""
+    import os
+    import threadpoolctl
+    if _threads["max"] is None:
+        _threads["max"] = os.cpu_count() or 1
+    want = _threads["max"] if big else 1
+    if _threads["cur"] != want:
+        threadpoolctl.threadpool_limits(limits=want, user_api="blas")
+        _threads["cur"] = want
 
 
 def _clib():
@@ -96,6 +112,7 @@ class SupernodalCPUFactor(object):
                 ms = nrow[s]
                 rs = ms - ns
                 panel = Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+                _set_blas_threads(ms * ns > SMALL_WORK)
                 Up = np.zeros((rs, rs), order='F') if rs else None
                 for c in plan.children[s]:
                     Uc = U.pop(c)
@@ -114,10 +131,10 @@ class SupernodalCPUFactor(object):
                     if rs:
                         panel[1:, 0] /= r
                 else:
-                    c11, info = lapack.dpotrf(panel[:ns, :], lower=1, clean=0, overwrite_a=0)
+                    c11, info = lapack.dpotrf(panel[:ns, :], lower=1, clean=1, overwrite_a=0)
                     if info != 0:
                         raise NotPositiveDefinite("non-positive pivot at column %d" % (f + info - 1))
-                    panel[:ns, :] = np.tril(c11)
+                    panel[:ns, :] = c11
                     if rs:
                         panel[ns:, :] = blas.dtrsm(1.0, c11, panel[ns:, :], side=1, lower=1, trans_a=1)
                 if rs:
@@ -125,6 +142,7 @@ class SupernodalCPUFactor(object):
                     U[s] = blas.dsyrk(-1.0, L21, beta=1.0, c=Up, lower=1, overwrite_c=1)
                 else:
                     U[s] = None
+        _set_blas_threads(True)
 
     def P(self):
         return self.plan.a['perm'].copy()
@@ -159,21 +177,29 @@ class SupernodalCPUFactor(object):
         return sp.csc_matrix((np.concatenate(vv), np.concatenate(ri), colptr), shape=(n, n))
 
     def _sweeps(self, Xp, forward=True, backward=True):
+        """Supernodal forward / backward substitution on a C-ordered (n x k) block.  BLAS sees the block as its
+        transpose (k x n, Fortran order), so the rows of one supernode are a contiguous column block and the
+        triangular solves run in place without copies."""
         a = self.plan.a
         lib = _clib()
         first, nrow, lptr, rowptr = a['sn_first'], a['sn_nrow'], a['sn_lptr'], a['sn_rowptr']
         nsuper = self.plan.sym.nsuper
         k = Xp.shape[1]
+        XT = Xp.T                                          # (k x n) F-contiguous view
         if forward:
             for s in range(nsuper):                       # ascending ids = children before parents
                 f = first[s]
                 ns = first[s + 1] - f
                 ms = nrow[s]
                 panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
-                xt = blas.dtrsm(1.0, panel[:ns, :], Xp[f:f + ns, :], lower=1)
-                Xp[f:f + ns, :] = xt
+                _set_blas_threads(ms * ns > SMALL_WORK)
+                xt = XT[:, f:f + ns]
+                if ns == 1:
+                    xt /= panel[0, 0]
+                else:                                      # x' := x' L11^-T
+                    blas.dtrsm(1.0, panel[:ns, :], xt, side=1, lower=1, trans_a=1, overwrite_b=1)
                 if ms > ns:
-                    u = np.ascontiguousarray(panel[ns:, :] @ xt)
+                    u = np.ascontiguousarray((xt @ panel[ns:, :].T).T)      # (rs x k) C-order
                     rows = a['rows'][rowptr[s] + ns:rowptr[s + 1]]
                     lib.oracle_scatter_sub_rows(_p(Xp), _p(rows), rows.size, _p(u), k)
         if backward:
@@ -182,13 +208,17 @@ class SupernodalCPUFactor(object):
                 ns = first[s + 1] - f
                 ms = nrow[s]
                 panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
-                xt = Xp[f:f + ns, :]
+                _set_blas_threads(ms * ns > SMALL_WORK)
+                xt = XT[:, f:f + ns]
                 if ms > ns:
                     rows = a['rows'][rowptr[s] + ns:rowptr[s + 1]]
                     gb = np.empty((rows.size, k))
                     lib.oracle_gather_rows(_p(Xp), _p(rows), rows.size, _p(gb), k)
-                    xt = xt - panel[ns:, :].T @ gb
-                Xp[f:f + ns, :] = blas.dtrsm(1.0, panel[:ns, :], xt, lower=1, trans_a=1)
+                    xt -= gb.T @ panel[ns:, :]
+                if ns == 1:
+                    xt /= panel[0, 0]
+                else:                                      # x' := x' L11^-1
+                    blas.dtrsm(1.0, panel[:ns, :], xt, side=1, lower=1, trans_a=0, overwrite_b=1)
         return Xp
 
     def __call__(self, b):
@@ -197,6 +227,7 @@ class SupernodalCPUFactor(object):
         perm = self.plan.a['perm']
         Xp = np.ascontiguousarray((b[:, None] if one else b)[perm])
         self._sweeps(Xp)
+        _set_blas_threads(True)
         out = np.empty_like(Xp)
         out[perm] = Xp
         return out[:, 0] if one else out
@@ -213,7 +244,9 @@ class SupernodalCPUFactor(object):
             ms = nrow[s]
             rows = a['rows'][rowptr[s]:rowptr[s + 1]]
             panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+            _set_blas_threads(ms * ns > SMALL_WORK)
             out[rows] += panel @ Z[f:f + ns]
+        _set_blas_threads(True)
         res = np.empty_like(out)
         res[a['perm']] = out
         return res

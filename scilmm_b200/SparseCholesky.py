@@ -86,7 +86,8 @@ class SparseCholesky(object):
     32-bit row indices and 64-bit pointers).  ordering_method: 'nesdis' / 'metis' (nested dissection),
     'natural', or pass `perm` (perm[new] = old) to force a permutation (parity mode: L is unique given P).
     rng: 'numpy' draws probe vectors from the global numpy stream exactly like the reference (:50);
-         'device' draws them on the GPU (distribution-equivalent, not stream-identical).
+         'device' draws them on the GPU (distribution-equivalent, not stream-identical);
+         'host_buffer' takes them from `probe_source(n, sim_num)` (a host array / pinned tensor).
     """
 
     def __init__(self, use_long=False, mode='supernodal', ordering_method='nesdis', perm=None, rng='numpy'):
@@ -95,6 +96,7 @@ class SparseCholesky(object):
         self._ordering_method = ordering_method
         self._perm = perm
         self.rng = rng
+        self.probe_source = None      # callable(n, sim_num) -> host block, used when rng == 'host_buffer'
         self._engines = {}
         self._sessions = {}
         self.timings = {}
@@ -203,10 +205,14 @@ class RemlSession(object):
         if Z is None:
             if self.functor.rng == 'numpy':
                 Z = _eng.to_device(np.random.randn(self.n, sim_num), torch)
+            elif self.functor.rng == 'host_buffer':       # caller-supplied host block (pinned tensor or ndarray)
+                Z = self.functor.probe_source(self.n, sim_num)
             else:
                 Z = torch.randn(self.n, sim_num, dtype=torch.float64, device="cuda")
-        elif not torch.is_tensor(Z):
+        if not torch.is_tensor(Z):
             Z = _eng.to_device(np.asarray(Z, dtype=np.float64), torch)
+        elif not Z.is_cuda:
+            Z = Z.to("cuda", non_blocking=True)
         if col_end is not None or col_begin:
             Z = Z[:, col_begin:col_end].contiguous()
         U = self.eng.lmul(Z)

@@ -53,6 +53,9 @@ SIGNATURES = {
     "slmm_chol_solve": (C.c_int, [vp, vp, i32, i32]),
     "slmm_chol_lmul": (C.c_int, [vp, vp, vp, i32]),
     "slmm_chol_export_L": (C.c_int, [vp, vp, vp, vp]),
+    "slmm_launch_count": (C.c_int, [C.POINTER(i64), i32]),
+    "slmm_chol_set_profiling": (C.c_int, [vp, i32]),
+    "slmm_chol_get_profile": (C.c_int, [vp, vp, vp, vp]),
     "slmm_symbolic_create": (C.c_int, [i32, vp, vp, i32, vp, pp]),
     "slmm_symbolic_destroy": (C.c_int, [vp]),
     "slmm_symbolic_stats": (C.c_int, [vp, vp, vp]),

@@ -24,6 +24,7 @@ namespace slmm {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const std::string& last_error() { return g_last_error; }
+int64_t g_launch_count = 0;
 
 constexpr int NBO = 256;   // outer block: columns updated together with K = NBO
 
@@ -147,6 +148,7 @@ struct Launch {
   int32_t count;    // ops / items
   int32_t grid;     // CTAs
   int32_t child_parity;
+  double flops;     // dense flops issued by this launch (0 for pulls)
 };
 
 constexpr int BIG_SMEM = 2 * 16 * (128 + 4) * 2 * 8;
@@ -186,7 +188,9 @@ struct PhaseBuilder {
   }
   void flush(Schedule& sch) {
     if (!potrf.empty()) {
-      sch.launches.push_back({Launch::POTRF, (int64_t)sch.potrf.size(), (int32_t)potrf.size(), (int32_t)potrf.size(), 0});
+      double pf = 0;
+      for (const PotrfOp& o : potrf) pf += 2.0 * o.nb * o.nb * o.nb / 3.0;
+      sch.launches.push_back({Launch::POTRF, (int64_t)sch.potrf.size(), (int32_t)potrf.size(), (int32_t)potrf.size(), 0, pf});
       sch.potrf.insert(sch.potrf.end(), potrf.begin(), potrf.end());
     }
     for (int pass = 0; pass < 2; pass++) {
@@ -194,6 +198,7 @@ struct PhaseBuilder {
       if (v.empty()) continue;
       const int T = pass == 0 ? 128 : 64;
       int64_t tiles = 0;
+      double lf = 0;
       for (GemmOp& op : v) {
         op.tiles_m = (op.M + T - 1) / T;
         op.tiles_n = (op.N + T - 1) / T;
@@ -201,10 +206,11 @@ struct PhaseBuilder {
         tiles += (int64_t)op.tiles_m * op.tiles_n;
         double f = 2.0 * op.M * op.N * op.K;
         sch.flops += (op.flags & GF_LOWER) ? 0.5 * f : f;
+        lf += (op.flags & GF_LOWER) ? 0.5 * f : f;
       }
       if (tiles > 2000000000LL) throw std::runtime_error("too many tiles in one phase");
       sch.launches.push_back({pass == 0 ? Launch::GEMM_BIG : Launch::GEMM_SMALL, (int64_t)sch.gemm.size(),
-                              (int32_t)v.size(), (int32_t)tiles, 0});
+                              (int32_t)v.size(), (int32_t)tiles, 0, lf});
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
     big.clear(); small.clear(); potrf.clear();
@@ -258,6 +264,10 @@ struct slmm_chol {
   std::vector<EntryMap> maps;
   std::map<int, std::unique_ptr<SolvePlan>> plans;
   bool factored = false;
+  bool profiling = false;
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+  double prof_flops[6] = {0, 0, 0, 0, 0, 0};
+  int64_t prof_n[6] = {0, 0, 0, 0, 0, 0};
   size_t bytes = 0;
   int64_t exported_nnz = 0;
 
@@ -268,32 +278,58 @@ struct slmm_chol {
 
 namespace slmm {
 
+static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const DevSym& ds, double* X,
+                       double* const* vec_arena, const int64_t* d_vptr, int nrhs) {
+  switch (L.kind) {
+    case Launch::POTRF:
+      potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM>>>(sch.d_potrf + L.off, h->d_info);
+      break;
+    case Launch::GEMM_BIG:
+      gemm_tiles_kernel<128, 128, 2, 4><<<L.grid, 256, BIG_SMEM>>>(sch.d_gemm + L.off, L.count);
+      break;
+    case Launch::GEMM_SMALL:
+      gemm_tiles_kernel<64, 64, 2, 2><<<L.grid, 128, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
+      break;
+    case Launch::PULL_MAT:
+      extend_add_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
+                                                    h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
+      break;
+    case Launch::PULL_VEC:
+      vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, X, vec_arena[L.child_parity],
+                                                  vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
+      break;
+    default:
+      break;
+  }
+}
+
 static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena, const int64_t* d_vptr,
                          int nrhs) {
   const DevSym ds = h->devsym();
-  for (const Launch& L : sch.launches) {
-    switch (L.kind) {
-      case Launch::POTRF:
-        potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM>>>(sch.d_potrf + L.off, h->d_info);
-        break;
-      case Launch::GEMM_BIG:
-        gemm_tiles_kernel<128, 128, 2, 4><<<L.grid, 256, BIG_SMEM>>>(sch.d_gemm + L.off, L.count);
-        break;
-      case Launch::GEMM_SMALL:
-        gemm_tiles_kernel<64, 64, 2, 2><<<L.grid, 128, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
-        break;
-      case Launch::PULL_MAT:
-        extend_add_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
-                                                      h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
-        break;
-      case Launch::PULL_VEC:
-        vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, X, vec_arena[L.child_parity],
-                                                    vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
-        break;
-      default:
-        break;
+  if (!h->profiling) {
+    for (const Launch& L : sch.launches) launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs);
+  } else {
+    // per-launch CUDA events on the launching stream (serialises nothing: same stream order), summed per kind
+    const size_t nl = sch.launches.size();
+    std::vector<cudaEvent_t> ev(nl + 1);
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaEventRecord(ev[0], 0));
+    for (size_t i = 0; i < nl; i++) {
+      launch_one(h, sch, sch.launches[i], ds, X, vec_arena, d_vptr, nrhs);
+      CUDA_OK(cudaEventRecord(ev[i + 1], 0));
     }
+    CUDA_OK(cudaEventSynchronize(ev[nl]));
+    for (size_t i = 0; i < nl; i++) {
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      const int k = (int)sch.launches[i].kind;
+      h->prof_ms[k] += ms;
+      h->prof_flops[k] += sch.launches[i].flops;
+      h->prof_n[k] += 1;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
   }
+  g_launch_count += (int64_t)sch.launches.size();
   CUDA_OK(cudaGetLastError());
 }
 
@@ -314,7 +350,7 @@ static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_k
     }
   }
   const int cnt = (int)(sch.pull.size() - off);
-  if (cnt > 0) sch.launches.push_back({kind, off, cnt, 0, (level + 1) & 1});
+  if (cnt > 0) sch.launches.push_back({kind, off, cnt, 0, (level + 1) & 1, 0.0});
 }
 
 static void build_factor_schedule(slmm_chol* h) {
@@ -341,7 +377,7 @@ static void build_factor_schedule(slmm_chol* h) {
         const int64_t ld = ms;
         if (kind == 0) {
           pb.potrf.push_back({P + c0 + c0 * ld, inv, (int32_t)ld, nb, f + c0, 0});
-          sch.flops += (double)nb * nb * nb / 3.0;
+          sch.flops += (double)nb * nb * nb / 3.0;   // counted as nb^3/3 multiply-adds pairs
         } else if (kind == 1) {
           // rows below the diagonal block:  X = X * inv^T   (in place, one tile column)
           pb.add(make_op(P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, inv, 1, NBI, ms - c1, nb, nb, 0));
@@ -633,6 +669,7 @@ int slmm_chol_add_values(slmm_chol_t* h, int32_t map_id, const double* d_values,
   if (m.nnz > 0) {
     const int grid = (int)std::min<int64_t>((m.nnz + 255) / 256, 148 * 16);
     scatter_axpy_kernel<<<grid, 256>>>(m.d_map, d_values, sigma, h->Lx, m.nnz);
+    g_launch_count++;
   }
   CUDA_OK(cudaGetLastError());
   h->factored = false;
@@ -665,6 +702,7 @@ int slmm_chol_logdet(slmm_chol_t* h, double* out) {
   if (!h->factored) throw std::invalid_argument("factorize first");
   const int grid = std::min(1024, (h->S.n + 255) / 256);
   logdet_kernel<<<grid, 256>>>(h->Lx, h->d_col2sn, h->d_sn_first, h->d_sn_nrow, h->d_sn_lptr, h->S.n, h->d_partial);
+  g_launch_count++;
   std::vector<double> part(grid);
   CUDA_OK(cudaMemcpy(part.data(), h->d_partial, grid * sizeof(double), cudaMemcpyDeviceToHost));
   double s = 0;
@@ -686,6 +724,7 @@ int slmm_chol_solve(slmm_chol_t* h, double* d_B, int32_t nrhs, int32_t mode) {
   if (mode == 0 || mode == 1) run_schedule(h, pl->fwd, pl->X, pl->arena, pl->d_vptr, nrhs);
   if (mode == 0 || mode == 2) run_schedule(h, pl->bwd, pl->X, pl->arena, pl->d_vptr, nrhs);
   gather_rows_kernel<<<grid, 256>>>(pl->X, d_B, h->d_perm, n, nrhs, 1);
+  g_launch_count += 2;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
   SLMM_CATCH
@@ -702,6 +741,7 @@ int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrh
   run_schedule(h, pl->lmul, pl->X2, pl->arena, pl->d_vptr, nrhs);
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
   gather_rows_kernel<<<grid, 256>>>(pl->X2, d_out, h->d_perm, n, nrhs, 1);
+  g_launch_count++;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
   SLMM_CATCH
@@ -727,6 +767,25 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* colptr, int32_t* rowidx, double*
   colptr[S.n] = q;
   return SLMM_OK;
   SLMM_CATCH
+}
+
+int slmm_launch_count(int64_t* out, int32_t reset) {
+  if (out) *out = g_launch_count;
+  if (reset) g_launch_count = 0;
+  return SLMM_OK;
+}
+
+int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on) {
+  if (!h) return SLMM_ERR_INVALID;
+  h->profiling = on != 0;
+  for (int k = 0; k < 6; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
+  return SLMM_OK;
+}
+
+int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6) {
+  if (!h || !ms6 || !flops6 || !n6) return SLMM_ERR_INVALID;
+  for (int k = 0; k < 6; k++) { ms6[k] = h->prof_ms[k]; flops6[k] = h->prof_flops[k]; n6[k] = h->prof_n[k]; }
+  return SLMM_OK;
 }
 
 struct slmm_symbolic { Symbolic S; };

@@ -12,6 +12,7 @@
 namespace slmm {
 
 void set_last_error(const std::string& msg);
+extern int64_t g_launch_count;   // kernels launched by this library since the last reset
 
 struct CudaError : std::runtime_error {
   explicit CudaError(const std::string& m) : std::runtime_error(m) {}

@@ -293,6 +293,7 @@ static void launch_group(slmm_matset* ms, const int* members, const double* d_y,
     }
   CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst.data(), NV * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
   reduce_partials_kernel<<<NV, 256>>>(part, grid, NV, ms->d_dst, d_out);
+  g_launch_count += 2;
   // the copy above must not be overwritten by the next group before the kernel ran: d_dst is consumed in
   // stream order and the next memcpy is also stream-ordered (pageable source is staged synchronously).
 }
@@ -430,6 +431,7 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
       const int32_t dst[2] = {2 * K + i * K + j, 2 * K + K * K + i * K + j};
       CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
       reduce_partials_kernel<<<2, 256>>>(part, grid, 2, ms->d_dst, d_out);
+      g_launch_count += 2;
     }
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
@@ -466,6 +468,7 @@ static int spmm_impl(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t nc
   else { SPMM_CASE(8) }
 #undef SPMM_CASE
   if (dot) reduce_partials_kernel<<<ncols, 256>>>(part, grid, ncols, nullptr, d_out);
+  g_launch_count += dot ? 2 : 1;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
 }

@@ -282,6 +282,16 @@ class CholEngine(object):
         check(lib().slmm_chol_lmul(self._h, Z2.data_ptr(), out.data_ptr(), int(Z2.shape[1])))
         return out if Z.dim() == 2 else out[:, 0]
 
+    def set_profiling(self, on):
+        check(lib().slmm_chol_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        """Per-kernel-kind device time (ms), issued flops and launch counts since set_profiling(True)."""
+        ms, fl, n = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)
+        check(lib().slmm_chol_get_profile(self._h, np_ptr(ms), np_ptr(fl), np_ptr(n)))
+        names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "other"]
+        return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(6)}
+
     def export_L(self):
         st = self.stats()
         nnz = st["exported_nnz"]
@@ -298,6 +308,12 @@ class CholEngine(object):
                 self._h = None
         except Exception:
             pass
+
+
+def launch_count(reset=False):
+    v = C.c_int64(0)
+    check(lib().slmm_launch_count(C.byref(v), 1 if reset else 0))
+    return v.value
 
 
 def gemm_selftest(M, N, K, lower=False, reps=5, seed=0):
