@@ -151,8 +151,10 @@ struct Launch {
   double flops;     // dense flops issued by this launch (0 for pulls)
 };
 
-constexpr int BIG_SMEM = 2 * 16 * (128 + 4) * 2 * 8;
-constexpr int SMALL_SMEM = 2 * 16 * (64 + 4) * 2 * 8;
+constexpr int BIG_STAGES = 4, SMALL_STAGES = 4;
+constexpr int BIG_SMEM = BIG_STAGES * 16 * (128 + 4) * 2 * 8 + 2 * BIG_STAGES * 8;
+constexpr int SMALL_SMEM = SMALL_STAGES * 16 * (64 + 4) * 2 * 8 + 2 * SMALL_STAGES * 8;
+constexpr int BIG_THREADS = 32 * (2 * 4 + 1), SMALL_THREADS = 32 * (2 * 2 + 1);
 
 struct Schedule {
   std::vector<Launch> launches;
@@ -278,6 +280,15 @@ struct slmm_chol {
 
 namespace slmm {
 
+static void init_kernel_attributes() {
+  static bool done = false;
+  if (done) return;
+  CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+  done = true;
+}
+
 static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const DevSym& ds, double* X,
                        double* const* vec_arena, const int64_t* d_vptr, int nrhs) {
   switch (L.kind) {
@@ -285,10 +296,10 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM>>>(sch.d_potrf + L.off, h->d_info);
       break;
     case Launch::GEMM_BIG:
-      gemm_tiles_kernel<128, 128, 2, 4><<<L.grid, 256, BIG_SMEM>>>(sch.d_gemm + L.off, L.count);
+      gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM>>>(sch.d_gemm + L.off, L.count);
       break;
     case Launch::GEMM_SMALL:
-      gemm_tiles_kernel<64, 64, 2, 2><<<L.grid, 128, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
+      gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
       break;
     case Launch::PULL_MAT:
       extend_add_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
@@ -553,12 +564,7 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
   opt.ordering = ordering;
   analyze(n, indptr, indices, user_perm, opt, h->S);
   const Symbolic& S = h->S;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
-    CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
-    attr_set = true;
-  }
+  init_kernel_attributes();
   // update-matrix and inverse-slot offsets
   h->uptr.assign(S.nsuper, 0);
   h->invptr.assign(S.nsuper + 1, 0);
@@ -848,7 +854,7 @@ int slmm_symbolic_entry_map(const slmm_symbolic_t* h, const int32_t* indptr, con
 int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,
                        int32_t lower, int32_t reps, float* ms_out) {
   SLMM_TRY
-  CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
+  init_kernel_attributes();
   Schedule sch;
   PhaseBuilder pb;
   pb.add(make_op(d_C, 1, M, d_A, 1, M, d_B, 1, N, M, N, K, lower ? GF_LOWER : 0));

@@ -46,21 +46,48 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// GEMM tiles: one CTA per TM x TN tile of C.  K is consumed in slabs of KS through a two-stage shared
-// memory ring (register-staged prefetch).  Shared tiles are stored [k][m] with a +4 pad so that the DMMA
-// fragment loads (8 rows x 4 k per quad layout) are bank-conflict free.
-template <int TM, int TN, int NWM, int NWN>
-__global__ void __launch_bounds__(32 * NWM * NWN) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
-  constexpr int NT = 32 * NWM * NWN;
+// GEMM tiles: one CTA per TM x TN tile of C, warp-specialised.
+//   * NWM*NWN compute warps: LDS fragment loads + DMMA only (their instruction stream stays tensor-dense);
+//   * one producer warp: streams K in slabs of KS=16 into a STAGES-deep shared-memory ring with 8-byte cp.async
+//     (LDGSTS: no register staging, zero-fill for ragged edges, any leading dimension, gathered rows);
+//   * full/empty mbarriers per stage (cp.async.mbarrier.arrive.noinc on the producer side), no __syncthreads in
+//     the main loop, so compute warps never wait for each other's address arithmetic.
+// Shared tiles are stored [k][m] with a +4 pad: the DMMA fragment loads (8 rows x 4 k per quad) are conflict free.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+
+template <int TM, int TN, int NWM, int NWN, int STAGES>
+__global__ void __launch_bounds__(32 * (NWM * NWN + 1)) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
+  constexpr int NCW = NWM * NWN;           // compute warps
   constexpr int KS = 16;
   constexpr int WM = TM / NWM, WN = TN / NWN;
   constexpr int MI = WM / 8, NI = WN / 8;
   constexpr int LDA = TM + 4, LDB = TN + 4;
-  constexpr int EA = TM * KS / NT, EB = TN * KS / NT;
-  static_assert(TM * KS % NT == 0 && TN * KS % NT == 0, "tile/threads mismatch");
+  static_assert(TM % 32 == 0 && TN % 32 == 0, "producer mapping needs 32-row chunks");
   extern __shared__ double smem[];
-  double* As = smem;                      // [2][KS][LDA]
-  double* Bs = smem + 2 * KS * LDA;       // [2][KS][LDB]
+  double* As = smem;                           // [STAGES][KS][LDA]
+  double* Bs = smem + STAGES * KS * LDA;       // [STAGES][KS][LDB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Bs + STAGES * KS * LDB);   // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                                       // [STAGES]
 
   // locate the operation this tile belongs to
   int lo = 0, hi = nops - 1;
@@ -69,80 +96,101 @@ __global__ void __launch_bounds__(32 * NWM * NWN) gemm_tiles_kernel(const GemmOp
     int mid = (lo + hi + 1) >> 1;
     if (ops[mid].tile_start <= tile) lo = mid; else hi = mid - 1;
   }
-  const GemmOp op = ops[lo];
+  const GemmOp& op = ops[lo];
   const int local = tile - op.tile_start;
-  const int tm = local % op.tiles_m, tn = local / op.tiles_m;
-  const int tm0 = tm * TM, tn0 = tn * TN;
-  if ((op.flags & GF_LOWER) && tm0 + TM <= tn0) return;   // tile entirely above the diagonal
+  const int tiles_m = op.tiles_m;
+  const int tm0 = (local % tiles_m) * TM, tn0 = (local / tiles_m) * TN;
+  const int flags = op.flags;
+  if ((flags & GF_LOWER) && tm0 + TM <= tn0) return;   // tile entirely above the diagonal (whole CTA exits)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = op.M, N = op.N, K = op.K;
+  const int nslab = (K + KS - 1) / KS;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 32); mbar_init(empty_bar + s, NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    // ------------------------------------------------------------------ producer warp
+    const int Mrem = M - tm0, Nrem = N - tn0;
+    const int64_t a_si = op.a_si, a_sk = op.a_sk, b_sj = op.b_sj, b_sk = op.b_sk;
+    const int32_t* kidx = op.a_kidx;
+    const bool a_kcontig = (a_sk == 1 && kidx == nullptr && a_si != 1);
+    const bool b_kcontig = (b_sk == 1 && b_sj != 1);
+    const double* Abase = op.A + (int64_t)tm0 * a_si;
+    const double* Bbase = op.B + (int64_t)tn0 * b_sj;
+    for (int s = 0; s < nslab; s++) {
+      const int stage = s % STAGES, use = s / STAGES;
+      if (use > 0) mbar_wait(empty_bar + stage, (use - 1) & 1);
+      const int k0 = s * KS;
+      double* as = As + stage * KS * LDA;
+      double* bs = Bs + stage * KS * LDB;
+      if (!a_kcontig) {          // lanes along the rows of the tile: 32 consecutive rows per copy instruction
+#pragma unroll 1
+        for (int k = 0; k < KS; k++) {
+          const bool kok = k0 + k < K;
+          const int64_t kk = (kok && kidx) ? (int64_t)kidx[k0 + k] : (int64_t)(k0 + k);
+          const double* src = Abase + kk * a_sk + (int64_t)lane * a_si;
+          double* dst = as + k * LDA + lane;
+#pragma unroll
+          for (int c = 0; c < TM / 32; c++) {
+            const bool ok = kok && (lane + 32 * c < Mrem);
+            cp_async8(dst + 32 * c, ok ? src + (int64_t)(32 * c) * a_si : Abase, ok ? 8 : 0);
+          }
+        }
+      } else {                   // k is the unit-stride dimension: 16 consecutive k of 2 rows per copy instruction
+        const int k = lane & 15, r = lane >> 4;
+        const bool kok = k0 + k < K;
+#pragma unroll 4
+        for (int c = 0; c < TM / 2; c++) {
+          const int i = 2 * c + r;
+          const bool ok = kok && i < Mrem;
+          cp_async8(as + k * LDA + i, ok ? Abase + (int64_t)i * a_si + (k0 + k) : Abase, ok ? 8 : 0);
+        }
+      }
+      if (!b_kcontig) {
+#pragma unroll 1
+        for (int k = 0; k < KS; k++) {
+          const bool kok = k0 + k < K;
+          const double* src = Bbase + (int64_t)(k0 + k) * b_sk + (int64_t)lane * b_sj;
+          double* dst = bs + k * LDB + lane;
+#pragma unroll
+          for (int c = 0; c < TN / 32; c++) {
+            const bool ok = kok && (lane + 32 * c < Nrem);
+            cp_async8(dst + 32 * c, ok ? src + (int64_t)(32 * c) * b_sj : Bbase, ok ? 8 : 0);
+          }
+        }
+      } else {
+        const int k = lane & 15, r = lane >> 4;
+        const bool kok = k0 + k < K;
+#pragma unroll 4
+        for (int c = 0; c < TN / 2; c++) {
+          const int j = 2 * c + r;
+          const bool ok = kok && j < Nrem;
+          cp_async8(bs + k * LDB + j, ok ? Bbase + (int64_t)j * b_sj + (k0 + k) : Bbase, ok ? 8 : 0);
+        }
+      }
+      mbar_cp_async_arrive(full_bar + stage);    // arrives (once per lane) when this lane's copies have landed
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- compute warps
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp % NWM) * WM, wn0 = (warp / NWM) * WN;
-  const int Mrem = op.M - tm0, Nrem = op.N - tn0;
-  const bool a_kcontig = (op.a_sk == 1 && op.a_kidx == nullptr && op.a_si != 1);
-  const bool b_kcontig = (op.b_sk == 1 && op.b_sj != 1);
-  const double* Abase = op.A + (int64_t)tm0 * op.a_si;
-  const double* Bbase = op.B + (int64_t)tn0 * op.b_sj;
-
   double acc[MI][NI][2];
 #pragma unroll
   for (int mi = 0; mi < MI; mi++)
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-  double ra[EA], rb[EB];
-  auto load_slab = [&](int k0) {
-#pragma unroll
-    for (int e = 0; e < EA; e++) {
-      const int q = e * NT + tid;
-      int i, k;
-      if (a_kcontig) { k = q % KS; i = q / KS; } else { i = q % TM; k = q / TM; }
-      double v = 0.0;
-      if (i < Mrem && k0 + k < op.K) {
-        const int64_t kk = op.a_kidx ? (int64_t)op.a_kidx[k0 + k] : (int64_t)(k0 + k);
-        v = Abase[(int64_t)i * op.a_si + kk * op.a_sk];
-      }
-      ra[e] = v;
-    }
-#pragma unroll
-    for (int e = 0; e < EB; e++) {
-      const int q = e * NT + tid;
-      int j, k;
-      if (b_kcontig) { k = q % KS; j = q / KS; } else { j = q % TN; k = q / TN; }
-      double v = 0.0;
-      if (j < Nrem && k0 + k < op.K) v = Bbase[(int64_t)j * op.b_sj + (int64_t)(k0 + k) * op.b_sk];
-      rb[e] = v;
-    }
-  };
-  auto store_slab = [&](int stage) {
-    double* as = As + stage * KS * LDA;
-    double* bs = Bs + stage * KS * LDB;
-#pragma unroll
-    for (int e = 0; e < EA; e++) {
-      const int q = e * NT + tid;
-      int i, k;
-      if (a_kcontig) { k = q % KS; i = q / KS; } else { i = q % TM; k = q / TM; }
-      as[k * LDA + i] = ra[e];
-    }
-#pragma unroll
-    for (int e = 0; e < EB; e++) {
-      const int q = e * NT + tid;
-      int j, k;
-      if (b_kcontig) { k = q % KS; j = q / KS; } else { j = q % TN; k = q / TN; }
-      bs[k * LDB + j] = rb[e];
-    }
-  };
-
-  const int nslab = (op.K + KS - 1) / KS;
-  if (nslab > 0) {
-    load_slab(0);
-    store_slab(0);
-  }
-  __syncthreads();
   for (int s = 0; s < nslab; s++) {
-    if (s + 1 < nslab) load_slab((s + 1) * KS);
-    const double* as = As + (s & 1) * KS * LDA + wm0 + g;
-    const double* bs = Bs + (s & 1) * KS * LDB + wn0 + g;
+    const int stage = s % STAGES;
+    mbar_wait(full_bar + stage, (s / STAGES) & 1);
+    const double* as = As + stage * KS * LDA + wm0 + g;
+    const double* bs = Bs + stage * KS * LDB + wn0 + g;
 #pragma unroll
     for (int kk = 0; kk < KS; kk += 4) {
       double af[MI], bf[NI];
@@ -155,23 +203,25 @@ __global__ void __launch_bounds__(32 * NWM * NWN) gemm_tiles_kernel(const GemmOp
 #pragma unroll
         for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
-    if (s + 1 < nslab) store_slab((s + 1) & 1);
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + stage);     // this warp no longer reads the stage
   }
 
   // epilogue: C = [C] +/- acc, optionally only on/below the diagonal of the region
-  const bool accum = op.flags & GF_ACCUM, neg = op.flags & GF_NEG, lower = op.flags & GF_LOWER;
+  const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG, lower = flags & GF_LOWER;
+  double* Cb = op.C;
+  const int64_t c_si = op.c_si, c_sj = op.c_sj;
 #pragma unroll
   for (int mi = 0; mi < MI; mi++) {
     const int i = tm0 + wm0 + mi * 8 + g;
-    if (i >= op.M) continue;
+    if (i >= M) continue;
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int j = tn0 + wn0 + ni * 8 + 2 * t + h;
-        if (j >= op.N || (lower && i < j)) continue;
-        double* cp = op.C + (int64_t)i * op.c_si + (int64_t)j * op.c_sj;
+        if (j >= N || (lower && i < j)) continue;
+        double* cp = Cb + (int64_t)i * c_si + (int64_t)j * c_sj;
         double v = neg ? -acc[mi][ni][h] : acc[mi][ni][h];
         if (accum) v += *cp;
         *cp = v;
