@@ -111,6 +111,9 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, dou
 int slmm_launch_count(int64_t* out, int32_t reset);
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on);
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6);
+/* per-launch records of the profiled runs (time, issued flops, kind, CTAs or work items); *n_out = available */
+int slmm_chol_get_launch_profile(const slmm_chol_t* h, int64_t max_n, int64_t* n_out, float* ms, double* flops,
+                                 int32_t* kind, int32_t* grid);
 
 /* Host-only view of the symbolic analysis (no CUDA device needed): used by the host-logic tests and to size a
  * problem before touching the GPU.  i_out as slmm_chol_stats i[0..8] plus i[9]=total rows entries; the array

@@ -56,6 +56,7 @@ SIGNATURES = {
     "slmm_launch_count": (C.c_int, [C.POINTER(i64), i32]),
     "slmm_chol_set_profiling": (C.c_int, [vp, i32]),
     "slmm_chol_get_profile": (C.c_int, [vp, vp, vp, vp]),
+    "slmm_chol_get_launch_profile": (C.c_int, [vp, i64, C.POINTER(i64), vp, vp, vp, vp]),
     "slmm_symbolic_create": (C.c_int, [i32, vp, vp, i32, vp, pp]),
     "slmm_symbolic_destroy": (C.c_int, [vp]),
     "slmm_symbolic_stats": (C.c_int, [vp, vp, vp]),

@@ -26,7 +26,7 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 const std::string& last_error() { return g_last_error; }
 int64_t g_launch_count = 0;
 
-constexpr int NBO = 256;   // outer block: columns updated together with K = NBO
+constexpr int NBO = 512;   // outer block: columns updated together with K = NBO
 
 struct PullItem { int32_t p, c0, c1; };
 
@@ -207,8 +207,12 @@ struct PhaseBuilder {
         op.tile_start = (int32_t)tiles;
         tiles += (int64_t)op.tiles_m * op.tiles_n;
         double f = 2.0 * op.M * op.N * op.K;
-        sch.flops += (op.flags & GF_LOWER) ? 0.5 * f : f;
-        lf += (op.flags & GF_LOWER) ? 0.5 * f : f;
+        if (op.flags & GF_LOWER) {       // entries on/below the diagonal of an M x N region (M >= N)
+          const double nn = std::min(op.M, op.N);
+          f = 2.0 * op.K * ((double)op.M * op.N - nn * (nn - 1) / 2.0);
+        }
+        sch.flops += f;
+        lf += f;
       }
       if (tiles > 2000000000LL) throw std::runtime_error("too many tiles in one phase");
       sch.launches.push_back({pass == 0 ? Launch::GEMM_BIG : Launch::GEMM_SMALL, (int64_t)sch.gemm.size(),
@@ -270,6 +274,9 @@ struct slmm_chol {
   double prof_ms[6] = {0, 0, 0, 0, 0, 0};
   double prof_flops[6] = {0, 0, 0, 0, 0, 0};
   int64_t prof_n[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<float> prof_launch_ms;       // per launch of the last profiled schedule run
+  std::vector<double> prof_launch_flops;
+  std::vector<int32_t> prof_launch_kind, prof_launch_grid;
   size_t bytes = 0;
   int64_t exported_nnz = 0;
 
@@ -337,6 +344,10 @@ static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* c
       h->prof_ms[k] += ms;
       h->prof_flops[k] += sch.launches[i].flops;
       h->prof_n[k] += 1;
+      h->prof_launch_ms.push_back(ms);
+      h->prof_launch_flops.push_back(sch.launches[i].flops);
+      h->prof_launch_kind.push_back(k);
+      h->prof_launch_grid.push_back(sch.launches[i].kind <= Launch::GEMM_SMALL ? sch.launches[i].grid : sch.launches[i].count);
     }
     for (auto& e : ev) cudaEventDestroy(e);
   }
@@ -785,12 +796,27 @@ int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on) {
   if (!h) return SLMM_ERR_INVALID;
   h->profiling = on != 0;
   for (int k = 0; k < 6; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
+  h->prof_launch_ms.clear(); h->prof_launch_flops.clear(); h->prof_launch_kind.clear(); h->prof_launch_grid.clear();
   return SLMM_OK;
 }
 
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6) {
   if (!h || !ms6 || !flops6 || !n6) return SLMM_ERR_INVALID;
   for (int k = 0; k < 6; k++) { ms6[k] = h->prof_ms[k]; flops6[k] = h->prof_flops[k]; n6[k] = h->prof_n[k]; }
+  return SLMM_OK;
+}
+
+int slmm_chol_get_launch_profile(const slmm_chol_t* h, int64_t max_n, int64_t* n_out, float* ms, double* flops,
+                                 int32_t* kind, int32_t* grid) {
+  if (!h || !n_out) return SLMM_ERR_INVALID;
+  const int64_t n = (int64_t)h->prof_launch_ms.size();
+  *n_out = n;
+  for (int64_t i = 0; i < n && i < max_n; i++) {
+    if (ms) ms[i] = h->prof_launch_ms[i];
+    if (flops) flops[i] = h->prof_launch_flops[i];
+    if (kind) kind[i] = h->prof_launch_kind[i];
+    if (grid) grid[i] = h->prof_launch_grid[i];
+  }
   return SLMM_OK;
 }
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
 }
 
 template <int TM, int TN, int NWM, int NWN, int STAGES>
-__global__ void __launch_bounds__(32 * (NWM * NWN + 1)) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
+__global__ void __launch_bounds__(32 * (NWM * NWN + 1), 1) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
   constexpr int NCW = NWM * NWN;           // compute warps
   constexpr int KS = 16;
   constexpr int WM = TM / NWM, WN = TN / NWN;
@@ -207,78 +207,112 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + 1)) gemm_tiles_kernel(const 
     if (lane == 0) mbar_arrive(empty_bar + stage);     // this warp no longer reads the stage
   }
 
-  // epilogue: C = [C] +/- acc, optionally only on/below the diagonal of the region
+  // epilogue: C = [C] +/- acc, optionally only on/below the diagonal of the region.  The read-modify-write is
+  // done in batches of 2*NI*2 independent loads per thread (a load-use chain per element would serialise on
+  // the memory latency and cost more than the K loop for K = 64).
   const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG, lower = flags & GF_LOWER;
   double* Cb = op.C;
   const int64_t c_si = op.c_si, c_sj = op.c_sj;
+  constexpr int MB = 1;   // 9 warps share 4 register files of 16K: 168 registers per thread is the ceiling
 #pragma unroll
-  for (int mi = 0; mi < MI; mi++) {
-    const int i = tm0 + wm0 + mi * 8 + g;
-    if (i >= M) continue;
+  for (int mb = 0; mb < MI; mb += MB) {
+    double old[MB][NI][2];
+    bool ok[MB][NI][2];
 #pragma unroll
-    for (int ni = 0; ni < NI; ni++) {
+    for (int m2 = 0; m2 < MB; m2++) {
+      const int i = tm0 + wm0 + (mb + m2) * 8 + g;
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int j = tn0 + wn0 + ni * 8 + 2 * t + h;
-        if (j >= N || (lower && i < j)) continue;
-        double* cp = Cb + (int64_t)i * c_si + (int64_t)j * c_sj;
-        double v = neg ? -acc[mi][ni][h] : acc[mi][ni][h];
-        if (accum) v += *cp;
-        *cp = v;
+      for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int j = tn0 + wn0 + ni * 8 + 2 * t + h;
+          ok[m2][ni][h] = (i < M) && (j < N) && !(lower && i < j);
+          old[m2][ni][h] = 0.0;
+        }
+    }
+    if (accum) {
+#pragma unroll
+      for (int m2 = 0; m2 < MB; m2++) {
+        const int i = tm0 + wm0 + (mb + m2) * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int j = tn0 + wn0 + ni * 8 + 2 * t + h;
+            if (ok[m2][ni][h]) old[m2][ni][h] = Cb[(int64_t)i * c_si + (int64_t)j * c_sj];
+          }
       }
+    }
+#pragma unroll
+    for (int m2 = 0; m2 < MB; m2++) {
+      const int i = tm0 + wm0 + (mb + m2) * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int j = tn0 + wn0 + ni * 8 + 2 * t + h;
+          const double a = acc[mb + m2][ni][h];
+          if (ok[m2][ni][h]) Cb[(int64_t)i * c_si + (int64_t)j * c_sj] = old[m2][ni][h] + (neg ? -a : a);
+        }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Diagonal-block Cholesky + inverse.  One CTA (256 threads) per block; the block lives in shared memory.
+//   Cholesky: right-looking, one barrier per column.  Thread (row = tid % 64, part = tid / 64) updates the
+//             entries (row, k), k = j+1+part, j+5+part, ... with the still unscaled column j and 1/l_jj.
+//   inverse : row recurrence X[i,:] = (e_i - L[i,:i] X[:i,:]) / l_ii; thread (part = tid % 4, col = tid / 4)
+//             sums a quarter of the products, quad shuffle-reduce, one barrier per row.
 // A non-positive pivot records 1 + global column in *info (smallest failing column wins).
 __global__ void __launch_bounds__(256) potrf_inv_kernel(const PotrfOp* __restrict__ ops, int* __restrict__ info) {
   extern __shared__ double potrf_smem[];
   double (*S)[NBI + 1] = reinterpret_cast<double (*)[NBI + 1]>(potrf_smem);
   double (*X)[NBI + 1] = reinterpret_cast<double (*)[NBI + 1]>(potrf_smem + NBI * (NBI + 1));
-  __shared__ int fail;
+  __shared__ double dinv[NBI];
   const PotrfOp op = ops[blockIdx.x];
   const int nb = op.nb, tid = threadIdx.x;
-  if (tid == 0) fail = 0;
   for (int q = tid; q < NBI * NBI; q += 256) {
     const int i = q % NBI, j = q / NBI;
     S[i][j] = (i < nb && j < nb && i >= j) ? op.blk[i + (int64_t)j * op.ld] : 0.0;
     X[i][j] = 0.0;
   }
   __syncthreads();
-  for (int j = 0; j < nb; j++) {
-    const double d = S[j][j];
-    if (!(d > 0.0)) {
-      if (tid == 0) { fail = 1; atomicMin(info, op.colbase + j + 1); }
-      break;                                   // uniform: every thread reads the same S[j][j]
+  {
+    const int row = tid & 63, part = tid >> 6;
+    for (int j = 0; j < nb; j++) {
+      const double d = S[j][j];
+      if (!(d > 0.0)) {                          // uniform: every thread reads the same value
+        if (tid == 0) atomicMin(info, op.colbase + j + 1);
+        return;
+      }
+      const double r = sqrt(d), rinv = 1.0 / r;
+      const double lij = S[row][j] * rinv;       // rows <= j read zeros / stale values and never use them
+      if (row > j) {
+#pragma unroll 4
+        for (int k = j + 1 + part; k <= row; k += 4) S[row][k] -= lij * (S[k][j] * rinv);
+      }
+      __syncthreads();                           // column j fully read, trailing block fully updated
+      if (part == 0) {
+        if (row > j) S[row][j] = lij;
+        else if (row == j) { S[j][j] = r; dinv[j] = rinv; }
+      }
+      // no barrier needed here: the next column step reads columns > j only, the writes above touch column j
     }
-    const double r = sqrt(d);
-    __syncthreads();
-    if (tid == 0) S[j][j] = r;
-    for (int i = j + 1 + tid; i < nb; i += 256) S[i][j] /= r;
-    __syncthreads();
-    // trailing update of the lower triangle: S[i][k] -= S[i][j] * S[k][j], j < k <= i
-    const int m = nb - j - 1;
-    for (int q = tid; q < m * m; q += 256) {
-      const int i = j + 1 + q % m, k = j + 1 + q / m;
-      if (k <= i) S[i][k] -= S[i][j] * S[k][j];
-    }
-    __syncthreads();
   }
   __syncthreads();
-  if (fail) return;
-  // inverse of the lower-triangular block, one column per thread, zero-padded so every thread walks the
-  // same k range (broadcast reads of S, conflict-free reads of X)
-  if (tid < nb) {
-    const int c = tid;
+  {
+    const int part = tid & 3, c = tid >> 2;
     for (int i = 0; i < nb; i++) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; k++) s -= S[i][k] * X[k][c];
-      X[i][c] = (i >= c) ? s / S[i][i] : 0.0;
+      double s = 0.0;
+#pragma unroll 8
+      for (int k = c + part; k < i; k += 4) s += S[i][k] * X[k][c];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0 && c <= i && c < nb) X[i][c] = ((i == c ? 1.0 : 0.0) - s) * dinv[i];
+      __syncthreads();
     }
   }
-  __syncthreads();
   for (int q = tid; q < NBI * NBI; q += 256) {
     const int i = q % NBI, j = q / NBI;
     if (i < nb && j < nb && i >= j) op.blk[i + (int64_t)j * op.ld] = S[i][j];

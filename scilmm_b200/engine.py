@@ -292,6 +292,16 @@ class CholEngine(object):
         names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "other"]
         return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(6)}
 
+    def launch_profile(self):
+        """(ms, flops, kind, grid) arrays, one entry per launch of the profiled schedule runs."""
+        n = C.c_int64(0)
+        check(lib().slmm_chol_get_launch_profile(self._h, 0, C.byref(n), None, None, None, None))
+        ms, fl = np.zeros(n.value, np.float32), np.zeros(n.value)
+        kind, grid = np.zeros(n.value, np.int32), np.zeros(n.value, np.int32)
+        check(lib().slmm_chol_get_launch_profile(self._h, n.value, C.byref(n), np_ptr(ms), np_ptr(fl), np_ptr(kind),
+                                                 np_ptr(grid)))
+        return ms, fl, kind, grid
+
     def export_L(self):
         st = self.stats()
         nnz = st["exported_nnz"]
