@@ -53,11 +53,18 @@ __device__ __forceinline__ int lower_bound_dev(const int32_t* a, int n, int v) {
   return lo;
 }
 
-// Parent-pull extend-add of the children's update matrices.  One warp owns target columns [c0,c1) of one
-// parent front and walks the children in fixed order, so no two warps ever write the same entry.
-__global__ void extend_add_kernel(const PullItem* __restrict__ items, int nitems, DevSym S, double* __restrict__ Lx,
-                                  const double* __restrict__ arena_child, double* __restrict__ arena_parent) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// Parent-pull extend-add of the children's update matrices.  One group of TPI threads (a warp for small parents,
+// a whole CTA for large ones) owns target columns [c0,c1) of one parent front and walks the children in fixed
+// order, so no two groups ever write the same entry (atomics-free, deterministic).  Rows are processed four at a
+// time per thread with all loads issued before the stores: rel[] is strictly increasing, so the four targets are
+// distinct and the read-modify-write chains are independent.
+template <int TPI>
+__global__ void __launch_bounds__(TPI < 128 ? 128 : TPI) extend_add_kernel(const PullItem* __restrict__ items, int nitems,
+                                                                         DevSym S, double* __restrict__ Lx,
+                                                                         const double* __restrict__ arena_child,
+                                                                         double* __restrict__ arena_parent) {
+  constexpr int GROUPS = (TPI < 128 ? 128 : TPI) / TPI;
+  const int w = blockIdx.x * GROUPS + threadIdx.x / TPI, lane = threadIdx.x % TPI;
   if (w >= nitems) return;
   const PullItem it = items[w];
   const int p = it.p;
@@ -68,19 +75,21 @@ __global__ void extend_add_kernel(const PullItem* __restrict__ items, int nitems
     const int c = S.child_idx[q];
     const int nsc = S.sn_first[c + 1] - S.sn_first[c], rsc = S.sn_nrow[c] - nsc;
     if (rsc == 0) continue;
-    const int32_t* relc = S.rel + S.sn_rowptr[c] + nsc;
+    const int32_t* __restrict__ relc = S.rel + S.sn_rowptr[c] + nsc;
     const double* Uc = arena_child + S.sn_uptr[c];
     const int ta = lower_bound_dev(relc, rsc, it.c0), tb = lower_bound_dev(relc, rsc, it.c1);
     for (int tt = ta; tt < tb; tt++) {
       const int pc = relc[tt];
-      const double* src = Uc + (int64_t)tt * rsc;
-      if (pc < nsp) {
-        double* dst = panel + (int64_t)pc * msp;
-        for (int u = tt + lane; u < rsc; u += 32) dst[relc[u]] += src[u];
-      } else {
-        double* dst = Up + (int64_t)(pc - nsp) * rsp - nsp;
-        for (int u = tt + lane; u < rsc; u += 32) dst[relc[u]] += src[u];
+      const double* __restrict__ src = Uc + (int64_t)tt * rsc;
+      double* dst = pc < nsp ? panel + (int64_t)pc * msp : Up + (int64_t)(pc - nsp) * rsp - nsp;
+      int u = tt + lane;
+      for (; u + 3 * TPI < rsc; u += 4 * TPI) {
+        const int r0 = relc[u], r1 = relc[u + TPI], r2 = relc[u + 2 * TPI], r3 = relc[u + 3 * TPI];
+        const double v0 = src[u], v1 = src[u + TPI], v2 = src[u + 2 * TPI], v3 = src[u + 3 * TPI];
+        const double d0 = dst[r0], d1 = dst[r1], d2 = dst[r2], d3 = dst[r3];
+        dst[r0] = d0 + v0; dst[r1] = d1 + v1; dst[r2] = d2 + v2; dst[r3] = d3 + v3;
       }
+      for (; u < rsc; u += TPI) dst[relc[u]] += src[u];
     }
   }
 }
@@ -143,7 +152,7 @@ __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __re
 
 // ---------------------------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, MEMSET } kind;
+  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG } kind;
   int64_t off;      // offset into the matching op array
   int32_t count;    // ops / items
   int32_t grid;     // CTAs
@@ -309,8 +318,12 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
       break;
     case Launch::PULL_MAT:
-      extend_add_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
-                                                    h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
+      extend_add_kernel<32><<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
+                                                        h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
+      break;
+    case Launch::PULL_MAT_BIG:
+      extend_add_kernel<256><<<L.count, 256>>>(sch.d_pull + L.off, L.count, ds, h->Lx, h->arena[L.child_parity],
+                                               h->arena[L.child_parity ^ 1]);
       break;
     case Launch::PULL_VEC:
       vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, X, vec_arena[L.child_parity],
@@ -355,13 +368,16 @@ static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* c
   CUDA_OK(cudaGetLastError());
 }
 
-static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_kind, Launch::Kind kind, int chunk) {
+static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_kind, Launch::Kind kind, int chunk,
+                           int min_rows = 0, int max_rows = 1 << 30) {
   // lo_kind: 0 -> targets [0, ns)   1 -> targets [ns, ms)   2 -> targets [0, ms)
+  // only parents with min_rows <= ms < max_rows are listed (lets the caller pick a kernel per size class)
   const int64_t off = (int64_t)sch.pull.size();
   for (int q = S.level_ptr[level]; q < S.level_ptr[level + 1]; q++) {
     const int p = S.level_sn[q];
     if (S.child_ptr[p + 1] == S.child_ptr[p]) continue;
     const int ns = S.sn_first[p + 1] - S.sn_first[p], ms = S.sn_nrow[p];
+    if (ms < min_rows || ms >= max_rows) continue;
     const int a = lo_kind == 1 ? ns : 0, b = lo_kind == 0 ? ns : ms;
     // do not cross the ns boundary inside one item (the kernels branch on it per target)
     for (int c0 = a; c0 < b;) {
@@ -380,7 +396,8 @@ static void build_factor_schedule(slmm_chol* h) {
   Schedule& sch = h->fact;
   PhaseBuilder pb;
   for (int d = S.nlevels - 1; d >= 0; d--) {
-    add_pull_items(sch, S, d, 0, Launch::PULL_MAT, 8);
+    add_pull_items(sch, S, d, 0, Launch::PULL_MAT, 8, 0, 512);
+    add_pull_items(sch, S, d, 0, Launch::PULL_MAT_BIG, 4, 512);
     int max_nib = 0;
     for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
       const int s = S.level_sn[q];
@@ -419,7 +436,8 @@ static void build_factor_schedule(slmm_chol* h) {
       }
       pb.flush(sch);
     }
-    add_pull_items(sch, S, d, 1, Launch::PULL_MAT, 8);
+    add_pull_items(sch, S, d, 1, Launch::PULL_MAT, 8, 0, 512);
+    add_pull_items(sch, S, d, 1, Launch::PULL_MAT_BIG, 4, 512);
   }
   sch.upload();
 }

@@ -289,7 +289,7 @@ class CholEngine(object):
         """Per-kernel-kind device time (ms), issued flops and launch counts since set_profiling(True)."""
         ms, fl, n = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)
         check(lib().slmm_chol_get_profile(self._h, np_ptr(ms), np_ptr(fl), np_ptr(n)))
-        names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "other"]
+        names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big"]
         return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(6)}
 
     def launch_profile(self):

@@ -11,11 +11,11 @@ A, T, D, F = P.numerator(ped["rel"]); keep, (A,) = P.drop_unrelated(A); nn = A.s
 mats = [A, P.epistasis(A), sp.eye(nn).tocsr()]
 rng = np.random.default_rng(1); cov = np.hstack([rng.standard_normal((nn, 10)), np.ones((nn, 1))]); y = rng.standard_normal(nn)
 chol = S.SparseCholesky(rng="device"); ses = chol._session(mats, cov, y); sig = np.array([0.3, 0.15, 0.55])
-names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "other"]
+names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big"]
 def report(tag):
     ms, fl, kind, grid = ses.eng.launch_profile()
     print("==", tag, "launches", ms.size, "total %.1f ms" % ms.sum())
-    for k in range(5):
+    for k in range(6):
         m = kind == k
         if m.sum() == 0: continue
         print("  %-10s n=%5d  %.1f ms  %.2f TFLOP/s" % (names[k], m.sum(), ms[m].sum(), fl[m].sum() / max(ms[m].sum(), 1e-9) / 1e9))
