@@ -69,6 +69,15 @@ int slmm_spmm(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, do
 int slmm_spmm_coldot(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, int32_t row_begin,
                      int32_t row_end, double* d_out);
 
+/* Fused variant for nk (1 or 2) matrices sharing one sparsity pattern (pattern ids from
+ * slmm_matset_pattern_id): one pass reads the indices and the gathered X rows once for all of them.
+ * d_dots[g*ncols + c] = sum_i X[i,c] (A_ks[g] X)[i,c];  columns c >= store_from of A_ks[g] X are also written to
+ * d_store[g][n][ncols - store_from] (C-ordered), which is what the REML trace correction needs
+ * (invV_C.T.dot(mats[i].dot(invV_C)), SparseCholesky.py:70).  ncols <= 160. */
+int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
+                           int32_t store_from, double* d_store, int32_t row_begin, int32_t row_end, double* d_dots);
+int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);
+
 /* ------------------------------------------------------------------ sparse Cholesky ------------------- */
 /* Symbolic analysis of a symmetric pattern given as CSR/CSC with both triangles (host arrays).  Replaces the
  * analyze half of sksparse.cholmod.cholesky (SparseCholesky.py:22-26); done once per pattern.

@@ -176,6 +176,7 @@ class RemlSession(object):
         self.C_host = np.asarray(covariates, dtype=np.float64)
         self.y_host = np.asarray(y, dtype=np.float64)
         self.setup_s = time.time() - t0
+        self._groups = None
         self.last = {}
 
     # K1 + K2
@@ -244,13 +245,29 @@ class RemlSession(object):
         comp1 = torch.zeros(K, dtype=torch.float64, device="cuda")
         comp2 = torch.zeros(K, dtype=torch.float64, device="cuda")
         gram = torch.zeros(K, c, c, dtype=torch.float64, device="cuda")
-        X = torch.cat([W, Vir.unsqueeze(1)], dim=1).contiguous()
-        for k in range(K):
-            d = self.matset.coldot(k, X)
-            comp1[k] = d[:-1].sum()
-            comp2[k] = d[-1]
-            if reml:
-                gram[k] = ViC.t() @ self.matset.spmm(k, ViC)
+        # one fused pass per pattern group over X = [W | V^-1 r | V^-1 C]: column quadratic forms for the probes and
+        # the residual, and A_k (V^-1 C) written out for the c x c REML trace term
+        s_loc = W.shape[1]
+        cols = [W, Vir.unsqueeze(1)] + ([ViC] if reml else [])
+        X = torch.cat(cols, dim=1).contiguous()
+        store_from = s_loc + 1 if reml else None
+        if self._groups is None:
+            self._groups = self.matset.pattern_groups(2)
+        if X.shape[1] <= 160:
+            for ks in self._groups:
+                dots, stored = self.matset.coldot_multi(ks, X, store_from)
+                for g, k in enumerate(ks):
+                    comp1[k] = dots[g, :s_loc].sum()
+                    comp2[k] = dots[g, s_loc]
+                    if reml:
+                        gram[k] = ViC.t() @ stored[g]
+        else:
+            for k in range(K):
+                d = self.matset.coldot(k, X[:, :s_loc + 1].contiguous())
+                comp1[k] = d[:-1].sum()
+                comp2[k] = d[-1]
+                if reml:
+                    gram[k] = ViC.t() @ self.matset.spmm(k, ViC)
         if world > 1:
             dist.all_reduce(comp1)
         comp1 = (comp1 / sim_num).cpu().numpy()

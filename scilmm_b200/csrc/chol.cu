@@ -132,6 +132,16 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, double* __res
   }
 }
 
+struct WBlock { int64_t off; int32_t n, pad; };
+
+// identity into every wide (outer-block) inverse slot, before the batched triangular inversion
+__global__ void init_identity_kernel(const WBlock* __restrict__ blocks, double* __restrict__ W) {
+  const WBlock b = blocks[blockIdx.x];
+  double* w = W + b.off;
+  const int64_t total = (int64_t)b.n * b.n;
+  for (int64_t q = threadIdx.x; q < total; q += blockDim.x) w[q] = (q % b.n == q / b.n) ? 1.0 : 0.0;
+}
+
 __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __restrict__ col2sn,
                               const int32_t* __restrict__ sn_first, const int32_t* __restrict__ sn_nrow,
                               const int64_t* __restrict__ sn_lptr, int n, double* __restrict__ partial) {
@@ -152,7 +162,7 @@ __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __re
 
 // ---------------------------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG } kind;
+  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG, INIT_W, REDUCE } kind;
   int64_t off;      // offset into the matching op array
   int32_t count;    // ops / items
   int32_t grid;     // CTAs
@@ -170,21 +180,33 @@ struct Schedule {
   std::vector<GemmOp> gemm;
   std::vector<PotrfOp> potrf;
   std::vector<PullItem> pull;
+  std::vector<ReduceOp> reduce;
+  int64_t ws_size = 0;            // doubles of split-K workspace (max over phases)
+  double* d_ws = nullptr;
+  ReduceOp* d_reduce = nullptr;
   GemmOp* d_gemm = nullptr;
   PotrfOp* d_potrf = nullptr;
   PullItem* d_pull = nullptr;
   double flops = 0;
   void upload() {
+    if (ws_size > 0) {              // patch workspace offsets into pointers
+      d_ws = dev_alloc<double>(ws_size);
+      for (GemmOp& op : gemm)
+        if (op.flags & GF_WS) { op.C = d_ws + (int64_t)(intptr_t)op.C; op.flags &= ~GF_WS; }
+      for (ReduceOp& r : reduce) r.ws = d_ws + (int64_t)(intptr_t)r.ws;
+    }
+    d_reduce = dev_upload(reduce.data(), reduce.size());
     d_gemm = dev_upload(gemm.data(), gemm.size());
     d_potrf = dev_upload(potrf.data(), potrf.size());
     d_pull = dev_upload(pull.data(), pull.size());
   }
   void release() {
-    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull);
-    d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr;
+    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_reduce);
+    d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr; d_ws = nullptr; d_reduce = nullptr;
   }
   size_t device_bytes() const {
-    return gemm.size() * sizeof(GemmOp) + potrf.size() * sizeof(PotrfOp) + pull.size() * sizeof(PullItem);
+    return gemm.size() * sizeof(GemmOp) + potrf.size() * sizeof(PotrfOp) + pull.size() * sizeof(PullItem) +
+           reduce.size() * sizeof(ReduceOp) + (size_t)ws_size * 8;
   }
 };
 
@@ -192,10 +214,45 @@ struct Schedule {
 struct PhaseBuilder {
   std::vector<GemmOp> big, small;
   std::vector<PotrfOp> potrf;
+  std::vector<ReduceOp> reduces;
+  int64_t ws_used = 0;
+  void push(const GemmOp& op) {
+    if (op.M > 64 && op.N > 64) big.push_back(op); else small.push_back(op);
+  }
   void add(GemmOp op) {
     if (op.M <= 0 || op.N <= 0 || op.K <= 0) return;
-    op.a_kidx = op.a_kidx;
-    if (op.M > 64 && op.N > 64) big.push_back(op); else small.push_back(op);
+    // Few output tiles but a long K (backward-solve gathers of fronts with few columns and many rows): split K
+    // across CTAs into workspace partials, reduced in fixed order by splitk_reduce_kernel.
+    const int T = (op.M > 64 && op.N > 64) ? 128 : 64;
+    const int64_t tiles = (int64_t)((op.M + T - 1) / T) * ((op.N + T - 1) / T);
+    if (!(op.flags & GF_LOWER) && tiles <= 148 && op.K >= 1024 && op.C != op.A) {
+      int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 256), std::max<int64_t>(2, 296 / tiles));
+      const int kc = (((op.K + S - 1) / S) + 15) / 16 * 16;
+      S = (op.K + kc - 1) / kc;
+      if (S >= 2) {
+        const int64_t mn = (int64_t)op.M * op.N;
+        ReduceOp r;
+        memset(&r, 0, sizeof(r));
+        r.C = op.C; r.c_si = op.c_si; r.c_sj = op.c_sj; r.M = op.M; r.N = op.N; r.S = S;
+        r.flags = op.flags & (GF_ACCUM | GF_NEG);
+        r.ws = (const double*)(intptr_t)ws_used;
+        reduces.push_back(r);
+        for (int c = 0; c < S; c++) {
+          GemmOp part = op;
+          const int k0 = c * kc;
+          part.K = std::min(kc, op.K - k0);
+          if (op.a_kidx) part.a_kidx = op.a_kidx + k0; else part.A = op.A + (int64_t)k0 * op.a_sk;
+          part.B = op.B + (int64_t)k0 * op.b_sk;
+          part.C = (double*)(intptr_t)(ws_used + (int64_t)c * mn);
+          part.c_si = 1; part.c_sj = op.M;
+          part.flags = GF_WS;
+          push(part);
+        }
+        ws_used += (int64_t)S * mn;
+        return;
+      }
+    }
+    push(op);
   }
   void flush(Schedule& sch) {
     if (!potrf.empty()) {
@@ -228,7 +285,18 @@ struct PhaseBuilder {
                               (int32_t)v.size(), (int32_t)tiles, 0, lf});
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
-    big.clear(); small.clear(); potrf.clear();
+    if (!reduces.empty()) {
+      int64_t blocks = 0;
+      for (ReduceOp& r : reduces) {
+        r.block_start = (int32_t)blocks;
+        blocks += ((int64_t)r.M * r.N + 255) / 256;
+      }
+      sch.launches.push_back({Launch::REDUCE, (int64_t)sch.reduce.size(), (int32_t)reduces.size(), (int32_t)blocks, 0, 0.0});
+      sch.reduce.insert(sch.reduce.end(), reduces.begin(), reduces.end());
+      sch.ws_size = std::max(sch.ws_size, ws_used);
+    }
+    big.clear(); small.clear(); potrf.clear(); reduces.clear();
+    ws_used = 0;
   }
 };
 
@@ -269,8 +337,12 @@ struct slmm_chol {
           *d_child_idx = nullptr, *d_col2sn = nullptr, *d_perm = nullptr;
   int64_t *d_sn_rowptr = nullptr, *d_sn_lptr = nullptr, *d_sn_uptr = nullptr;
   std::vector<int64_t> uptr, invptr;
+  std::vector<int64_t> wptr;          // [nsuper+1] offsets of the wide inverse blocks of each supernode
+  std::vector<WBlock> wblocks;
+  WBlock* d_wblocks = nullptr;
   double* Lx = nullptr;
   double* inv = nullptr;
+  double* W = nullptr;                // inverses of the NBO-wide diagonal blocks (supernodes wider than NBI)
   double* arena[2] = {nullptr, nullptr};
   int64_t arena_size[2] = {0, 0};
   int* d_info = nullptr;
@@ -280,9 +352,9 @@ struct slmm_chol {
   std::map<int, std::unique_ptr<SolvePlan>> plans;
   bool factored = false;
   bool profiling = false;
-  double prof_ms[6] = {0, 0, 0, 0, 0, 0};
-  double prof_flops[6] = {0, 0, 0, 0, 0, 0};
-  int64_t prof_n[6] = {0, 0, 0, 0, 0, 0};
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_flops[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<float> prof_launch_ms;       // per launch of the last profiled schedule run
   std::vector<double> prof_launch_flops;
   std::vector<int32_t> prof_launch_kind, prof_launch_grid;
@@ -328,6 +400,12 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
     case Launch::PULL_VEC:
       vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, X, vec_arena[L.child_parity],
                                                   vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
+      break;
+    case Launch::REDUCE:
+      splitk_reduce_kernel<<<L.grid, 256>>>(sch.d_reduce + L.off, L.count);
+      break;
+    case Launch::INIT_W:
+      init_identity_kernel<<<L.count, 256>>>(h->d_wblocks, h->W);
       break;
     default:
       break;
@@ -391,6 +469,28 @@ static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_k
   if (cnt > 0) sch.launches.push_back({kind, off, cnt, 0, (level + 1) & 1, 0.0});
 }
 
+// Outer (NBO-wide) diagonal block `ob` of supernode s: column range, and where its inverse lives.  A block made
+// of a single NBI block reuses the POTRF kernel's 64 x 64 inverse slot; wider blocks get their own slot in W.
+struct OuterBlock { int o0, nbo, ldw; double* winv; };
+static int num_outer(int ns) { return (ns + NBO - 1) / NBO; }
+static OuterBlock outer_block(const slmm_chol* h, int s, int ob) {
+  const Symbolic& S = h->S;
+  const int ns = S.sn_first[s + 1] - S.sn_first[s];
+  OuterBlock b;
+  b.o0 = ob * NBO;
+  b.nbo = std::min(ns, b.o0 + NBO) - b.o0;
+  if (b.nbo <= NBI) {
+    b.winv = h->inv + h->invptr[s] + (int64_t)(b.o0 / NBI) * NBI * NBI;
+    b.ldw = NBI;
+  } else {
+    int64_t off = h->wptr[s];
+    for (int q = 0; q < ob; q++) off += (int64_t)NBO * NBO;      // every earlier block of s is a full one
+    b.winv = h->W + off;
+    b.ldw = b.nbo;
+  }
+  return b;
+}
+
 static void build_factor_schedule(slmm_chol* h) {
   const Symbolic& S = h->S;
   Schedule& sch = h->fact;
@@ -439,6 +539,35 @@ static void build_factor_schedule(slmm_chol* h) {
     add_pull_items(sch, S, d, 1, Launch::PULL_MAT, 8, 0, 512);
     add_pull_items(sch, S, d, 1, Launch::PULL_MAT_BIG, 4, 512);
   }
+  // ---- batched triangular inversion of every NBO-wide diagonal block (all supernodes at once; off every front's
+  //      critical path).  W = I, then forward substitution by NBI blocks:  W[t,:] = inv_t W[t,:];
+  //      W[t+1:,:] -= L[t+1:,t] W[t,:].  The multi-RHS solves then need 2 GEMMs per 512 columns instead of per 64.
+  if (!h->wblocks.empty()) {
+    sch.launches.push_back({Launch::INIT_W, 0, (int32_t)h->wblocks.size(), (int32_t)h->wblocks.size(), 0, 0.0});
+    for (int t = 0; t < NBO / NBI; t++) {
+      for (int half = 0; half < 2; half++) {
+        for (int s2 = 0; s2 < S.nsuper; s2++) {
+          const int ns = S.sn_first[s2 + 1] - S.sn_first[s2];
+          if (ns <= NBI) continue;
+          double* P = h->Lx + S.sn_lptr[s2];
+          const int64_t ldp = S.sn_nrow[s2];
+          for (int ob = 0; ob < num_outer(ns); ob++) {
+            const OuterBlock b = outer_block(h, s2, ob);
+            if (b.nbo <= NBI || t * NBI >= b.nbo) continue;
+            const int r0 = t * NBI, nbt = std::min(NBI, b.nbo - r0), ncols = std::min(b.nbo, r0 + NBI);
+            double* inv64 = h->inv + h->invptr[s2] + (int64_t)((b.o0 + r0) / NBI) * NBI * NBI;
+            if (half == 0) {
+              pb.add(make_op(b.winv + r0, 1, b.ldw, inv64, 1, NBI, b.winv + r0, b.ldw, 1, nbt, ncols, nbt, 0));
+            } else if (r0 + nbt < b.nbo) {
+              pb.add(make_op(b.winv + r0 + nbt, 1, b.ldw, P + (b.o0 + r0 + nbt) + (int64_t)(b.o0 + r0) * ldp, 1, ldp,
+                             b.winv + r0, b.ldw, 1, b.nbo - r0 - nbt, ncols, nbt, GF_ACCUM | GF_NEG));
+            }
+          }
+        }
+        pb.flush(sch);
+      }
+    }
+  }
   sch.upload();
 }
 
@@ -473,70 +602,76 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
   pl->bytes = ((size_t)2 * n * nrhs + asz[0] + asz[1]) * 8;
   const int64_t R = nrhs;
   PhaseBuilder pb;
-  // ---------------- forward:  L y = b  (levels deepest first)
+  // ---------------- forward:  L y = b  (levels deepest first).  X holds b and the running updates, the solved
+  //                  blocks y land in X2 (out of place: Y = Winv * X per NBO-wide diagonal block).
   for (int d = S.nlevels - 1; d >= 0; d--) {
     add_pull_items(pl->fwd, S, d, 0, Launch::PULL_VEC, 4);
-    int max_nib = 0;
+    int max_nob = 0;
     for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
       const int s = S.level_sn[q];
-      max_nib = std::max(max_nib, (S.sn_first[s + 1] - S.sn_first[s] + NBI - 1) / NBI);
+      max_nob = std::max(max_nob, num_outer(S.sn_first[s + 1] - S.sn_first[s]));
     }
-    for (int ph = 0; ph < 2 * max_nib + 1; ph++) {
+    for (int ph = 0; ph < 2 * max_nob + 1; ph++) {
       for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
         const int s = S.level_sn[q];
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
-        const int nib = (ns + NBI - 1) / NBI;
+        const int nob = num_outer(ns);
         double* P = h->Lx + S.sn_lptr[s];
         const int64_t ld = ms;
         double* Xs = pl->X + (int64_t)f * R;
-        if (ph == 2 * nib) {                       // contribution block  u = -L21 y   (rs x nrhs)
+        double* Ys = pl->X2 + (int64_t)f * R;
+        if (ph == 2 * nob) {                       // contribution block  u = -L21 y   (rs x nrhs)
           if (rs > 0)
-            pb.add(make_op(pl->arena[d & 1] + vptr[s], 1, R, Xs, 1, R, P + ns, 1, ld, nrhs, rs, ns, GF_NEG));
+            pb.add(make_op(pl->arena[d & 1] + vptr[s], 1, R, Ys, 1, R, P + ns, 1, ld, nrhs, rs, ns, GF_NEG));
           continue;
         }
-        if (ph > 2 * nib) continue;
-        const int ib = ph / 2, c0 = ib * NBI, c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
-        double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
-        if (ph % 2 == 0) {                         // y_b = inv * x_b        (transposed view: X^T = X^T inv^T)
-          pb.add(make_op(Xs + c0 * R, 1, R, Xs + c0 * R, 1, R, inv, 1, NBI, nrhs, nb, nb, 0));
-        } else if (c1 < ns) {                      // x[c1:ns] -= L[c1:ns, c0:c1] y_b
-          pb.add(make_op(Xs + c1 * R, 1, R, Xs + c0 * R, 1, R, P + c1 + c0 * ld, 1, ld, nrhs, ns - c1, nb,
-                         GF_ACCUM | GF_NEG));
+        if (ph > 2 * nob) continue;
+        const OuterBlock b = outer_block(h, s, ph / 2);
+        const int o1 = b.o0 + b.nbo;
+        if (ph % 2 == 0) {                         // y_b = Winv * x_b      (transposed view: Y^T = X^T Winv^T)
+          pb.add(make_op(Ys + (int64_t)b.o0 * R, 1, R, Xs + (int64_t)b.o0 * R, 1, R, b.winv, 1, b.ldw, nrhs, b.nbo,
+                         b.nbo, 0));
+        } else if (o1 < ns) {                      // x[o1:ns] -= L[o1:ns, o0:o1] y_b
+          pb.add(make_op(Xs + (int64_t)o1 * R, 1, R, Ys + (int64_t)b.o0 * R, 1, R, P + o1 + (int64_t)b.o0 * ld, 1, ld,
+                         nrhs, ns - o1, b.nbo, GF_ACCUM | GF_NEG));
         }
       }
       pb.flush(pl->fwd);
     }
     add_pull_items(pl->fwd, S, d, 1, Launch::PULL_VEC, 4);
   }
-  // ---------------- backward:  L' x = y  (roots first); reads ancestors' final rows through the row lists
+  // ---------------- backward:  L' x = y  (roots first).  X2 holds y and the running updates, the solved blocks x
+  //                  land in X; ancestors' final rows are read from X through the row lists.
   for (int d = 0; d < S.nlevels; d++) {
-    int max_nib = 0;
+    int max_nob = 0;
     for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
       const int s = S.level_sn[q];
-      max_nib = std::max(max_nib, (S.sn_first[s + 1] - S.sn_first[s] + NBI - 1) / NBI);
+      max_nob = std::max(max_nob, num_outer(S.sn_first[s + 1] - S.sn_first[s]));
     }
-    for (int ph = 0; ph < 2 * max_nib + 1; ph++) {
+    for (int ph = 0; ph < 2 * max_nob + 1; ph++) {
       for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
         const int s = S.level_sn[q];
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
-        const int nib = (ns + NBI - 1) / NBI;
+        const int nob = num_outer(ns);
         double* P = h->Lx + S.sn_lptr[s];
         const int64_t ld = ms;
         double* Xs = pl->X + (int64_t)f * R;
-        if (ph == 0) {                             // x_top -= L21' x[rows below]   (gathered rows)
+        double* Ys = pl->X2 + (int64_t)f * R;
+        if (ph == 0) {                             // y_top -= L21' x[rows below]   (gathered rows of X)
           if (rs > 0)
-            pb.add(make_op(Xs, 1, R, pl->X, 1, R, P + ns, ld, 1, nrhs, ns, rs, GF_ACCUM | GF_NEG,
+            pb.add(make_op(Ys, 1, R, pl->X, 1, R, P + ns, ld, 1, nrhs, ns, rs, GF_ACCUM | GF_NEG,
                            h->d_rows + S.sn_rowptr[s] + ns));
           continue;
         }
-        const int step = ph - 1, r = step / 2;     // blocks in reverse order
-        if (r >= nib) continue;
-        const int ib = nib - 1 - r, c0 = ib * NBI, c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
-        double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
-        if (step % 2 == 0) {                       // x_b = inv' * x_b
-          pb.add(make_op(Xs + c0 * R, 1, R, Xs + c0 * R, 1, R, inv, NBI, 1, nrhs, nb, nb, 0));
-        } else if (c0 > 0) {                       // x[0:c0] -= L[c0:c1, 0:c0]' x_b
-          pb.add(make_op(Xs, 1, R, Xs + c0 * R, 1, R, P + c0, ld, 1, nrhs, c0, nb, GF_ACCUM | GF_NEG));
+        const int step = ph - 1, r = step / 2;     // outer blocks in reverse order
+        if (r >= nob) continue;
+        const OuterBlock b = outer_block(h, s, nob - 1 - r);
+        if (step % 2 == 0) {                       // x_b = Winv' * y_b
+          pb.add(make_op(Xs + (int64_t)b.o0 * R, 1, R, Ys + (int64_t)b.o0 * R, 1, R, b.winv, b.ldw, 1, nrhs, b.nbo,
+                         b.nbo, 0));
+        } else if (b.o0 > 0) {                     // y[0:o0] -= L[o0:o1, 0:o0]' x_b
+          pb.add(make_op(Ys, 1, R, Xs + (int64_t)b.o0 * R, 1, R, P + b.o0, ld, 1, nrhs, b.o0, b.nbo,
+                         GF_ACCUM | GF_NEG));
         }
       }
       pb.flush(pl->bwd);
@@ -608,10 +743,20 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
     h->arena_size[d & 1] = std::max(h->arena_size[d & 1], off);
   }
   h->exported_nnz = 0;
+  h->wptr.assign(S.nsuper + 1, 0);
   for (int s = 0; s < S.nsuper; s++) {
     const int64_t ns = S.sn_first[s + 1] - S.sn_first[s], ms = S.sn_nrow[s];
     h->invptr[s + 1] = h->invptr[s] + ((ns + NBI - 1) / NBI) * NBI * NBI;
     h->exported_nnz += ns * ms - ns * (ns - 1) / 2;
+    int64_t w = 0;
+    for (int ob = 0; ob < num_outer((int)ns); ob++) {
+      const int nbo = (int)std::min<int64_t>(ns, (int64_t)(ob + 1) * NBO) - ob * NBO;
+      if (nbo > NBI) {
+        h->wblocks.push_back({h->wptr[s] + w, nbo, 0});
+        w += (int64_t)nbo * nbo;
+      }
+    }
+    h->wptr[s + 1] = h->wptr[s] + w;
   }
   h->d_sn_first = dev_upload(S.sn_first.data(), S.sn_first.size());
   h->d_sn_nrow = dev_upload(S.sn_nrow.data(), S.sn_nrow.size());
@@ -626,13 +771,15 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
   h->d_sn_uptr = dev_upload(h->uptr.data(), h->uptr.size());
   h->Lx = dev_alloc<double>(S.lsize);
   h->inv = dev_alloc<double>(h->invptr[S.nsuper]);
+  h->W = dev_alloc<double>(h->wptr[S.nsuper]);
+  h->d_wblocks = dev_upload(h->wblocks.data(), h->wblocks.size());
   h->arena[0] = dev_alloc<double>(h->arena_size[0]);
   h->arena[1] = dev_alloc<double>(h->arena_size[1]);
   h->d_info = dev_alloc<int>(1);
   h->d_partial = dev_alloc<double>(1024);
   CUDA_OK(cudaMemset(h->Lx, 0, S.lsize * sizeof(double)));
   build_factor_schedule(h.get());
-  h->bytes = (S.lsize + h->invptr[S.nsuper] + h->arena_size[0] + h->arena_size[1]) * 8 +
+  h->bytes = (S.lsize + h->invptr[S.nsuper] + h->wptr[S.nsuper] + h->arena_size[0] + h->arena_size[1]) * 8 +
              (S.rows.size() * 2 + S.sn_first.size() * 8) * 4 + h->fact.device_bytes();
   CUDA_OK(cudaDeviceSynchronize());
   *out = h.release();
@@ -645,7 +792,7 @@ int slmm_chol_destroy(slmm_chol_t* h) {
   dev_free(h->d_sn_first); dev_free(h->d_sn_nrow); dev_free(h->d_rows); dev_free(h->d_rel);
   dev_free(h->d_child_ptr); dev_free(h->d_child_idx); dev_free(h->d_col2sn); dev_free(h->d_perm);
   dev_free(h->d_sn_rowptr); dev_free(h->d_sn_lptr); dev_free(h->d_sn_uptr);
-  dev_free(h->Lx); dev_free(h->inv); dev_free(h->arena[0]); dev_free(h->arena[1]);
+  dev_free(h->Lx); dev_free(h->inv); dev_free(h->W); dev_free(h->d_wblocks); dev_free(h->arena[0]); dev_free(h->arena[1]);
   dev_free(h->d_info); dev_free(h->d_partial);
   h->fact.release();
   for (auto& m : h->maps) dev_free(m.d_map);
@@ -755,10 +902,11 @@ int slmm_chol_solve(slmm_chol_t* h, double* d_B, int32_t nrhs, int32_t mode) {
   const int n = h->S.n;
   const int64_t total = (int64_t)n * nrhs;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
-  gather_rows_kernel<<<grid, 256>>>(d_B, pl->X, h->d_perm, n, nrhs, 0);
+  // forward consumes X and leaves y in X2; backward consumes X2 and leaves x in X
+  gather_rows_kernel<<<grid, 256>>>(d_B, mode == 2 ? pl->X2 : pl->X, h->d_perm, n, nrhs, 0);
   if (mode == 0 || mode == 1) run_schedule(h, pl->fwd, pl->X, pl->arena, pl->d_vptr, nrhs);
   if (mode == 0 || mode == 2) run_schedule(h, pl->bwd, pl->X, pl->arena, pl->d_vptr, nrhs);
-  gather_rows_kernel<<<grid, 256>>>(pl->X, d_B, h->d_perm, n, nrhs, 1);
+  gather_rows_kernel<<<grid, 256>>>(mode == 1 ? pl->X2 : pl->X, d_B, h->d_perm, n, nrhs, 1);
   g_launch_count += 2;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
@@ -813,7 +961,7 @@ int slmm_launch_count(int64_t* out, int32_t reset) {
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on) {
   if (!h) return SLMM_ERR_INVALID;
   h->profiling = on != 0;
-  for (int k = 0; k < 6; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
+  for (int k = 0; k < 8; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
   h->prof_launch_ms.clear(); h->prof_launch_flops.clear(); h->prof_launch_kind.clear(); h->prof_launch_grid.clear();
   return SLMM_OK;
 }

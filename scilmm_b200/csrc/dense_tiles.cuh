@@ -18,7 +18,7 @@ namespace slmm {
 constexpr int NBI = 64;   // diagonal block size (POTRF / inverse granularity)
 constexpr int POTRF_SMEM = 2 * NBI * (NBI + 1) * 8;
 
-enum GemmFlags { GF_LOWER = 1, GF_ACCUM = 2, GF_NEG = 4 };
+enum GemmFlags { GF_LOWER = 1, GF_ACCUM = 2, GF_NEG = 4, GF_WS = 8 /* C is an offset into the split-K workspace */ };
 
 struct GemmOp {
   double* C;
@@ -29,6 +29,15 @@ struct GemmOp {
   int32_t M, N, K;
   int32_t flags;
   int32_t tile_start, tiles_m, tiles_n, pad;
+};
+
+// Second half of a deterministic split-K GEMM: C (+/-)= sum over the S partial products parked in the workspace.
+struct ReduceOp {
+  double* C;
+  const double* ws;        // S consecutive M x N column-major partials
+  int64_t c_si, c_sj;
+  int32_t M, N, S, flags;
+  int32_t block_start, pad;
 };
 
 struct PotrfOp {
@@ -128,10 +137,15 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + 1), 1) gemm_tiles_kernel(con
       double* as = As + stage * KS * LDA;
       double* bs = Bs + stage * KS * LDB;
       if (!a_kcontig) {          // lanes along the rows of the tile: 32 consecutive rows per copy instruction
+        // gathered K index: one coalesced load of the slab's 16 row ids, broadcast by shuffle (a dependent
+        // scalar load per k would put ~16 memory latencies on the producer's critical path per slab)
+        int myk = 0;
+        if (kidx && lane < KS && k0 + lane < K) myk = kidx[k0 + lane];
 #pragma unroll 1
         for (int k = 0; k < KS; k++) {
           const bool kok = k0 + k < K;
-          const int64_t kk = (kok && kidx) ? (int64_t)kidx[k0 + k] : (int64_t)(k0 + k);
+          const int gk = __shfl_sync(0xffffffffu, myk, k);
+          const int64_t kk = kidx ? (int64_t)gk : (int64_t)(k0 + k);
           const double* src = Abase + kk * a_sk + (int64_t)lane * a_si;
           double* dst = as + k * LDA + lane;
 #pragma unroll
@@ -356,6 +370,26 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(const PotrfOp* __restric
     if (i < nb && jj < nb && i >= jj) op.blk[i + (int64_t)jj * op.ld] = Lf[i][jj];
     op.inv[i + jj * NBI] = (i < nb && jj < nb) ? X[i][jj] : 0.0;
   }
+}
+
+// fixed-order reduction of split-K partials (no atomics: results are bit-reproducible run to run)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceOp* __restrict__ ops, int nops) {
+  int lo = 0, hi = nops - 1;
+  const int blk = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (ops[mid].block_start <= blk) lo = mid; else hi = mid - 1;
+  }
+  const ReduceOp op = ops[lo];
+  const int64_t total = (int64_t)op.M * op.N;
+  const int64_t e = (int64_t)(blk - op.block_start) * 256 + threadIdx.x;
+  if (e >= total) return;
+  double sum = 0.0;
+  for (int s = 0; s < op.S; s++) sum += op.ws[(int64_t)s * total + e];
+  const int i = (int)(e % op.M), j = (int)(e / op.M);
+  double* cp = op.C + (int64_t)i * op.c_si + (int64_t)j * op.c_sj;
+  const double v = (op.flags & GF_NEG) ? -sum : sum;
+  *cp = (op.flags & GF_ACCUM) ? *cp + v : v;
 }
 
 }  // namespace slmm

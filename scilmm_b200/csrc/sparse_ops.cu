@@ -231,6 +231,83 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int32_t* __restrict__ i
   }
 }
 
+// SpMM + column quadratic forms for G matrices that share ONE sparsity pattern (e.g. IBD and its Hadamard
+// square): index stream and the gathered X rows - the dominant traffic, ncols*8 bytes per nonzero - are read
+// once for all G.  dots[g][c] = sum_i X[i,c] (A_g X)[i,c]; optionally (A_g X)[:, store_from:] is written out
+// (the few covariate columns whose full Gram matrix is needed, reference scilmm/SparseCholesky.py:70).
+template <int CPL, int G>
+__global__ void __launch_bounds__(256) spmm_group_kernel(const int32_t* __restrict__ indptr,
+                                                         const int32_t* __restrict__ indices, GroupArgs<G> vals,
+                                                         const double* __restrict__ X, int ncols, int row_begin,
+                                                         int row_end, int store_from, double* __restrict__ store,
+                                                         int64_t store_stride, double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nstore = ncols - store_from;
+  double dot[G][CPL];
+#pragma unroll
+  for (int g = 0; g < G; g++)
+#pragma unroll
+    for (int c = 0; c < CPL; c++) dot[g][c] = 0.0;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    double acc[G][CPL];
+#pragma unroll
+    for (int g = 0; g < G; g++)
+#pragma unroll
+      for (int c = 0; c < CPL; c++) acc[g][c] = 0.0;
+    for (int p0 = b; p0 < e; p0 += 32) {
+      const int pl = p0 + lane;
+      const int mycol = pl < e ? indices[pl] : 0;
+      double myval[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) myval[g] = pl < e ? vals.data[g][pl] : 0.0;
+      const int cnt = min(32, e - p0);
+      for (int k = 0; k < cnt; k++) {
+        const int col = __shfl_sync(0xffffffffu, mycol, k);
+        double v[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) v[g] = __shfl_sync(0xffffffffu, myval[g], k);
+        const double* xr = X + (int64_t)col * ncols;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+          const int j = lane + 32 * c;
+          if (j < ncols) {
+            const double x = xr[j];
+#pragma unroll
+            for (int g = 0; g < G; g++) acc[g][c] += v[g] * x;
+          }
+        }
+      }
+    }
+    const double* xi = X + (int64_t)row * ncols;
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const int j = lane + 32 * c;
+      if (j < ncols) {
+        const double x = xi[j];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          dot[g][c] += acc[g][c] * x;
+          if (j >= store_from) store[g * store_stride + (int64_t)row * nstore + (j - store_from)] = acc[g][c];
+        }
+      }
+    }
+  }
+  __shared__ double sh[8][32 * CPL];
+  for (int g = 0; g < G; g++) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CPL; c++) sh[warp][lane + 32 * c] = dot[g][c];
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncols; j += 256) {
+      double s2 = 0.0;
+      for (int w = 0; w < 8; w++) s2 += sh[w][j];
+      partial[((int64_t)blockIdx.x * G + g) * ncols + j] = s2;
+    }
+  }
+}
+
 }  // namespace slmm
 
 using namespace slmm;
@@ -296,6 +373,24 @@ static void launch_group(slmm_matset* ms, const int* members, const double* d_y,
   g_launch_count += 2;
   // the copy above must not be overwritten by the next group before the kernel ran: d_dst is consumed in
   // stream order and the next memcpy is also stream-ordered (pageable source is staged synchronously).
+}
+
+}  // namespace slmm
+
+namespace slmm {
+template <int CPL, int G>
+static void launch_spmm_group(slmm_matset* ms, const int32_t* ks, const double* d_X, int ncols, int store_from,
+                              double* d_store, int r0, int r1, double* d_dots) {
+  GroupArgs<G> v;
+  v.indptr = ms->m[ks[0]].indptr;
+  v.indices = ms->m[ks[0]].indices;
+  for (int g = 0; g < G; g++) v.data[g] = ms->m[ks[g]].data;
+  const int grid = he_grid(r1 - r0);
+  double* part = ms->partial((size_t)grid * G * ncols);
+  const int64_t stride = (int64_t)ms->n * (ncols - store_from);
+  spmm_group_kernel<CPL, G><<<grid, 256>>>(v.indptr, v.indices, v, d_X, ncols, r0, r1, store_from, d_store, stride, part);
+  reduce_partials_kernel<<<G * ncols, 256>>>(part, grid, G * ncols, nullptr, d_dots);
+  g_launch_count += 2;
 }
 
 }  // namespace slmm
@@ -484,6 +579,35 @@ int slmm_spmm_coldot(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t nc
   SLMM_TRY
   return spmm_impl(ms, k, d_X, ncols, r0, r1, d_out, true);
   SLMM_CATCH
+}
+
+int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
+                           int32_t store_from, double* d_store, int32_t r0, int32_t r1, double* d_dots) {
+  SLMM_TRY
+  if (!ms || !ks || !d_X || !d_dots || nk <= 0 || nk > 2 || ncols <= 0 || ncols > 160)
+    throw std::invalid_argument("slmm_spmm_coldot_multi: need 1 <= nk <= 2, ncols <= 160");
+  if (store_from < 0 || store_from > ncols || (store_from < ncols && !d_store)) throw std::invalid_argument("bad store range");
+  if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
+  for (int g = 0; g < nk; g++) {
+    if (ks[g] < 0 || ks[g] >= ms->K || !ms->m[ks[g]].data) throw std::invalid_argument("matrix not set");
+    if (ms->m[ks[g]].pattern != ms->m[ks[0]].pattern) throw std::invalid_argument("matrices must share one pattern");
+  }
+  const int cpl = (ncols + 31) / 32;
+#define GROUP_CASE(C)                                                                                       \
+  if (nk == 1) launch_spmm_group<C, 1>(ms, ks, d_X, ncols, store_from, d_store, r0, r1, d_dots);            \
+  else launch_spmm_group<C, 2>(ms, ks, d_X, ncols, store_from, d_store, r0, r1, d_dots);
+  if (cpl <= 1) { GROUP_CASE(1) } else if (cpl <= 2) { GROUP_CASE(2) } else if (cpl <= 3) { GROUP_CASE(3) }
+  else if (cpl <= 4) { GROUP_CASE(4) } else { GROUP_CASE(5) }
+#undef GROUP_CASE
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out) {
+  if (!ms || k < 0 || k >= ms->K || !out) return SLMM_ERR_INVALID;
+  *out = ms->m[k].pattern;
+  return SLMM_OK;
 }
 
 }  // extern "C"

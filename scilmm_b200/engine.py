@@ -204,6 +204,39 @@ class MatSet(object):
                 out[c0:c1] = o
         return out
 
+    def pattern_id(self, k):
+        v = C.c_int32(-1)
+        check(lib().slmm_matset_pattern_id(self._h, int(k), C.byref(v)))
+        return v.value
+
+    def pattern_groups(self, max_group=2):
+        """Lists of matrix indices sharing one pattern (at most max_group per list)."""
+        groups, out = {}, []
+        for k in range(self.K):
+            groups.setdefault(self.pattern_id(k), []).append(k)
+        for ks in groups.values():
+            for i in range(0, len(ks), max_group):
+                out.append(ks[i:i + max_group])
+        return out
+
+    def coldot_multi(self, ks, X, store_from=None, row_begin=0, row_end=None):
+        """Fused pass over matrices `ks` (same pattern): returns (dots [len(ks), ncols], stored [len(ks), n, ncols -
+        store_from] or None)."""
+        torch = _torch()
+        X2 = X.contiguous()
+        n, ncols = X2.shape
+        row_end = self.n if row_end is None else row_end
+        store_from = ncols if store_from is None else store_from
+        ks_arr = np.asarray(ks, dtype=np.int32)
+        dots = torch.empty(len(ks), ncols, dtype=torch.float64, device="cuda")
+        store = None
+        if store_from < ncols:
+            store = torch.zeros(len(ks), n, ncols - store_from, dtype=torch.float64, device="cuda")
+        check(lib().slmm_spmm_coldot_multi(self._h, len(ks), np_ptr(ks_arr), X2.data_ptr(), int(ncols), int(store_from),
+                                           store.data_ptr() if store is not None else None, int(row_begin),
+                                           int(row_end), dots.data_ptr()))
+        return dots, store
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -34,7 +34,8 @@ def eng():
 # ------------------------------------------------------------------------------------------ dense tiles
 @pytest.mark.parametrize("M,N,K,lower", [(64, 64, 64, False), (128, 128, 16, False), (200, 150, 37, False),
                                          (513, 257, 130, False), (300, 300, 64, True), (1000, 40, 64, False),
-                                         (7, 5, 3, False), (140, 777, 64, False)])
+                                         (7, 5, 3, False), (140, 777, 64, False), (128, 200, 5000, False),
+                                         (140, 60, 20011, False)])
 def test_dmma_gemm_tiles(eng, M, N, K, lower):
     err, ms, tf = eng.gemm_selftest(M, N, K, lower=lower, reps=1)
     assert err < 1e-11 * max(K, 1), (err, M, N, K)
@@ -110,6 +111,19 @@ def test_spmm_and_coldot(golden_c1mini, eng):
             assert rel_err(ms.coldot(k, Xd).cpu().numpy(), np.sum(ref * X, axis=0)) < 1e-12
     x1 = rng.standard_normal(g.n)
     assert rel_err(ms.spmm(1, eng.to_device(x1)).cpu().numpy(), mats[1].dot(x1)) < 1e-13
+    # fused pass over the two matrices that share a pattern (IBD and its Hadamard square)
+    assert ms.pattern_id(0) == ms.pattern_id(1) != ms.pattern_id(2)
+    assert sorted(map(tuple, ms.pattern_groups(2))) == [(0, 1), (2,)]
+    for ncols, store_from in ((5, 2), (140, 129), (64, None), (160, 150)):
+        X = rng.standard_normal((g.n, ncols))
+        Xd = eng.to_device(X)
+        for ks in ([0, 1], [2], [1]):
+            dots, stored = ms.coldot_multi(ks, Xd, store_from)
+            for gi, k in enumerate(ks):
+                ref = mats[k].dot(X)
+                assert rel_err(dots[gi].cpu().numpy(), np.sum(ref * X, axis=0)) < 1e-12
+                if store_from is not None:
+                    assert rel_err(stored[gi].cpu().numpy(), ref[:, store_from:]) < 1e-13
 
 
 # ------------------------------------------------------------------------------------------ factorization
