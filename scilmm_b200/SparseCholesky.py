@@ -21,6 +21,7 @@ import scipy.optimize as optimize
 import scipy.sparse as sparse
 
 from . import engine as _eng
+from . import sharding as _shard
 from ._lib import NotPositiveDefiniteError, SlmmError  # noqa: F401  (re-exported)
 
 LOG_2PI = np.log(2 * np.pi)
@@ -222,7 +223,6 @@ class RemlSession(object):
     def evaluate(self, sigmas, reml, sim_num, Z=None):
         """One REML evaluation: nll and d nll / d sigma  (reference :77-117 without the exp chain rule)."""
         torch = self.torch
-        dist = _dist()
         self.factor_at(sigmas)
         logdet = self.eng.logdet()
         ViC, chol, beta, Viy = self.fixed_effects()
@@ -234,11 +234,10 @@ class RemlSession(object):
         if reml:
             nll += 0.5 * 2 * np.sum(np.log(np.diag(chol[0])))
         # probe columns are sharded across ranks when torch.distributed is initialised
-        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        rank, world = _shard.rank_world()
         if Z is None and self.functor.rng == 'numpy' and world > 1:
             Z = np.random.randn(n, sim_num)            # every rank draws the same stream, keeps its slice
-        lo = (sim_num * rank) // world
-        hi = (sim_num * (rank + 1)) // world
+        lo, hi = _shard.column_block(sim_num, rank, world)
         W = self.probes(sim_num, Z, lo, hi) if world > 1 else self.probes(sim_num, Z)
         c = self.C.shape[1]
         K = self.K
@@ -268,8 +267,7 @@ class RemlSession(object):
                 comp2[k] = d[-1]
                 if reml:
                     gram[k] = ViC.t() @ self.matset.spmm(k, ViC)
-        if world > 1:
-            dist.all_reduce(comp1)
+        _shard.allreduce_sum_(comp1)                   # the only collective of an evaluation: K doubles
         comp1 = (comp1 / sim_num).cpu().numpy()
         comp2 = comp2.cpu().numpy()
         grad = 0.5 * (comp1 - comp2)
@@ -279,16 +277,6 @@ class RemlSession(object):
                 grad[k] -= 0.5 * np.trace(la.cho_solve(chol, gram_h[k]))
         self.last = dict(logdet=logdet, beta=beta, ViC=ViC, Vir=Vir, Viy=Viy, W=W, chol=chol)
         return nll, grad
-
-
-def _dist():
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return dist
-    except Exception:
-        pass
-    return None
 
 
 def _need_functor(cholesky_func):
@@ -474,15 +462,14 @@ def he_moments(mat_list, y, MQS=False, matset=None):
     torch = _eng.require_cuda()
     K, n = ms.K, ms.n
     y_dev = _eng.to_device(np.asarray(y, dtype=np.float64), torch)
-    dist = _dist()
-    if dist is None:
+    rank, world = _shard.rank_world()
+    if world == 1:
         out = ms.he_moments_device(y_dev).cpu().numpy()
-    else:       # row-block shard + one allreduce of 2K + 2K^2 doubles
-        rank, world = dist.get_rank(), dist.get_world_size()
-        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-        part = ms.he_moments_device(y_dev, lo, hi).clone()
-        dist.all_reduce(part)
-        out = part.cpu().numpy()
+    else:       # row blocks balanced by nonzeros + one all-reduce of 2K + 2K^2 doubles
+        big = max(range(K), key=lambda k: ms.nnz[k])
+        bounds = _shard.row_blocks_by_nnz(_eng.canonical_csr(mat_list[big]).indptr, world)
+        part = ms.he_moments_device(y_dev, int(bounds[rank]), int(bounds[rank + 1])).clone()
+        out = _shard.allreduce_sum_(part).cpu().numpy()
     q_off, q_diag, S_off, S_diag = _eng.MatSet.split_moments(out, K)
     if MQS:
         yy = float(np.dot(y, y))
