@@ -46,6 +46,7 @@ struct GroupArgs {
 template <int G>
 __global__ void __launch_bounds__(256) he_group_kernel(GroupArgs<G> a, const double* __restrict__ y, int row_begin,
                                                        int row_end, double* __restrict__ partial) {
+  constexpr int UN = 4;
   constexpr int NP = G * (G + 1) / 2;
   constexpr int NV = 2 * G + 2 * NP;
   double qo[G], qd[G], so[NP], sd[NP];
@@ -55,33 +56,52 @@ __global__ void __launch_bounds__(256) he_group_kernel(GroupArgs<G> a, const dou
   for (int p = 0; p < NP; p++) so[p] = sd[p] = 0.0;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
-    const int b = a.indptr[row], e = a.indptr[row + 1];
-    const double yi = y[row];
+  int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int nb = 0, ne = 0;
+  double nyi = 0.0;
+  if (row < row_end) { nb = a.indptr[row]; ne = a.indptr[row + 1]; nyi = y[row]; }
+  for (; row < row_end; row += warps) {
+    const int b = nb, e = ne;
+    const double yi = nyi;
+    if (row + warps < row_end) {         // row pointers of the next row are fetched under this row's loads
+      nb = a.indptr[row + warps]; ne = a.indptr[row + warps + 1]; nyi = y[row + warps];
+    }
     double rowacc[G];
 #pragma unroll
     for (int g = 0; g < G; g++) rowacc[g] = 0.0;
-    for (int p = b + lane; p < e; p += 32) {
-      const int col = a.indices[p];
-      const double yj = y[col];
-      double v[G];
+    // UN independent 32-entry chunks per trip: all index / value loads are issued before the dependent y gathers
+    // (memory-level parallelism; a single chunk in flight per warp leaves the HBM pipe three quarters empty)
+    for (int p0 = b + lane; p0 < e; p0 += 32 * UN) {
+      int col[UN];
+      double v[UN][G], yj[UN];
 #pragma unroll
-      for (int g = 0; g < G; g++) v[g] = a.data[g][p];
-      if (col != row) {
+      for (int u = 0; u < UN; u++) {
+        const int p = p0 + 32 * u;
+        col[u] = p < e ? __ldcs(a.indices + p) : -1;
 #pragma unroll
-        for (int g = 0; g < G; g++) rowacc[g] += v[g] * yj;
-        int q = 0;
+        for (int g = 0; g < G; g++) v[u][g] = p < e ? __ldcs(a.data[g] + p) : 0.0;
+      }
 #pragma unroll
-        for (int g = 0; g < G; g++)
+      for (int u = 0; u < UN; u++) yj[u] = col[u] >= 0 ? y[col[u]] : 0.0;
 #pragma unroll
-          for (int h = 0; h <= g; h++) so[q++] += v[g] * v[h];
-      } else {
-        int q = 0;
+      for (int u = 0; u < UN; u++) {
+        if (col[u] < 0) continue;
+        if (col[u] != row) {
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-          qd[g] += v[g] * yi * yi;
+          for (int g = 0; g < G; g++) rowacc[g] += v[u][g] * yj[u];
+          int q = 0;
 #pragma unroll
-          for (int h = 0; h <= g; h++) sd[q++] += v[g] * v[h];
+          for (int g = 0; g < G; g++)
+#pragma unroll
+            for (int h = 0; h <= g; h++) so[q++] += v[u][g] * v[u][h];
+        } else {
+          int q = 0;
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            qd[g] += v[u][g] * yi * yi;
+#pragma unroll
+            for (int h = 0; h <= g; h++) sd[q++] += v[u][g] * v[u][h];
+          }
         }
       }
     }
@@ -145,6 +165,109 @@ __global__ void __launch_bounds__(256) he_cross_kernel(const int32_t* __restrict
     double s = 0.0;
     for (int w = 0; w < 8; w++) s += sh[w][threadIdx.x];
     partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+// Short-row matrices (household indicator: ~2 entries per row): a warp per row would idle 30 lanes and put one
+// memory latency per row on every warp.  Thread per row instead; same outputs as he_group_kernel<1>.
+__global__ void __launch_bounds__(256) he_short_kernel(const int32_t* __restrict__ indptr,
+                                                       const int32_t* __restrict__ indices,
+                                                       const double* __restrict__ data, const double* __restrict__ y,
+                                                       int row_begin, int row_end, double* __restrict__ partial) {
+  double qo = 0.0, qd = 0.0, so = 0.0, sd = 0.0;
+  for (int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += gridDim.x * blockDim.x) {
+    const int b = indptr[row], e = indptr[row + 1];
+    const double yi = y[row];
+    double acc = 0.0;
+    for (int p = b; p < e; p++) {
+      const int col = indices[p];
+      const double v = data[p];
+      if (col != row) { acc += v * y[col]; so += v * v; } else { qd += v * yi * yi; sd += v * v; }
+    }
+    qo += acc * yi;
+  }
+  __shared__ double sh[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  qo = warp_sum(qo); qd = warp_sum(qd); so = warp_sum(so); sd = warp_sum(sd);
+  if (lane == 0) { sh[warp][0] = qo; sh[warp][1] = qd; sh[warp][2] = so; sh[warp][3] = sd; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s2 = 0.0;
+    for (int w = 0; w < 8; w++) s2 += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * 4 + threadIdx.x] = s2;
+  }
+}
+
+// Hadamard dot where one matrix has short rows: thread per row of the short matrix, binary search in the other.
+__global__ void __launch_bounds__(256) he_cross_short_kernel(const int32_t* __restrict__ sp_, const int32_t* __restrict__ si,
+                                                             const double* __restrict__ sx, const int32_t* __restrict__ lp,
+                                                             const int32_t* __restrict__ li, const double* __restrict__ lx,
+                                                             int row_begin, int row_end, double* __restrict__ partial) {
+  double off = 0.0, dg = 0.0;
+  for (int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += gridDim.x * blockDim.x) {
+    const int sb = sp_[row], se = sp_[row + 1], lb = lp[row], le = lp[row + 1];
+    for (int p = sb; p < se; p++) {
+      const int col = si[p];
+      int lo = lb, hi = le;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (li[mid] < col) lo = mid + 1; else hi = mid; }
+      if (lo < le && li[lo] == col) {
+        const double v = sx[p] * lx[lo];
+        if (col == row) dg += v; else off += v;
+      }
+    }
+  }
+  __shared__ double sh[8][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  off = warp_sum(off);
+  dg = warp_sum(dg);
+  if (lane == 0) { sh[warp][0] = off; sh[warp][1] = dg; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s2 = 0.0;
+    for (int w = 0; w < 8; w++) s2 += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s2;
+  }
+}
+
+// Hadamard dots between two pattern groups in one pass: every entry of the probe pattern is located once in the
+// target pattern (sorted rows, binary search) and multiplied with all GP x GT value pairs.
+// TPR = true: thread per probe row (short rows), false: warp per probe row.  partial: [GP*GT][off, diag] per CTA.
+template <int GP, int GT, bool TPR>
+__global__ void __launch_bounds__(256) he_cross_multi_kernel(GroupArgs<GP> pr, GroupArgs<GT> tg, int row_begin,
+                                                             int row_end, double* __restrict__ partial) {
+  constexpr int NV = GP * GT * 2;
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) acc[k] = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const int first = TPR ? gtid : (gtid >> 5), step = TPR ? gthreads : (gthreads >> 5);
+  for (int row = row_begin + first; row < row_end; row += step) {
+    const int sb = pr.indptr[row], se = pr.indptr[row + 1], lb = tg.indptr[row], le = tg.indptr[row + 1];
+    for (int p = sb + (TPR ? 0 : lane); p < se; p += (TPR ? 1 : 32)) {
+      const int col = pr.indices[p];
+      int lo = lb, hi = le;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (tg.indices[mid] < col) lo = mid + 1; else hi = mid; }
+      if (lo < le && tg.indices[lo] == col) {
+        const int d = col == row ? 1 : 0;
+#pragma unroll
+        for (int gp = 0; gp < GP; gp++)
+#pragma unroll
+          for (int gt = 0; gt < GT; gt++) acc[(gp * GT + gt) * 2 + d] += pr.data[gp][p] * tg.data[gt][lo];
+      }
+    }
+  }
+  __shared__ double sh[8][NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) sh[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s2 = 0.0;
+    for (int w = 0; w < 8; w++) s2 += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * NV + threadIdx.x] = s2;
   }
 }
 
@@ -499,6 +622,19 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
       if (!done[j] && ms->m[j].pattern == ms->m[k].pattern) { members[G++] = j; done[j] = 1; }
     for (int g0 = 0; g0 < G; g0 += 4) {           // at most 4 matrices fused per pass
       const int gn = std::min(4, G - g0);
+      const CsrDev& lead = ms->m[members[g0]];
+      if (gn == 1 && lead.nnz < (int64_t)8 * ms->n) {      // short rows: thread per row
+        const int rows = r1 - r0;
+        const int grid = std::max(1, std::min(148 * 8, (rows + 255) / 256));
+        double* part = ms->partial((size_t)grid * 4);
+        he_short_kernel<<<grid, 256>>>(lead.indptr, lead.indices, lead.data, d_y, r0, r1, part);
+        const int k0 = members[g0];
+        const int32_t dst[4] = {k0, K + k0, 2 * K + k0 * K + k0, 2 * K + K * K + k0 * K + k0};
+        CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
+        reduce_partials_kernel<<<4, 256>>>(part, grid, 4, ms->d_dst, d_out);
+        g_launch_count += 2;
+        continue;
+      }
       switch (gn) {
         case 1: launch_group<1>(ms, members + g0, d_y, r0, r1, d_out); break;
         case 2: launch_group<2>(ms, members + g0, d_y, r0, r1, d_out); break;
@@ -507,27 +643,73 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
       }
     }
   }
-  // pairs that were not covered by a fused pass
-  for (int i = 0; i < K; i++)
-    for (int j = 0; j < i; j++) {
-      bool fused = false;
-      if (ms->m[i].pattern == ms->m[j].pattern) {
-        // same group: fused only if they fell into the same chunk of 4
-        int pi = 0, pj = 0, c = 0;
-        for (int t = 0; t < K; t++)
-          if (ms->m[t].pattern == ms->m[i].pattern) { if (t == i) pi = c; if (t == j) pj = c; c++; }
-        fused = (pi / 4 == pj / 4);
-      }
-      if (fused) continue;
-      const int grid = he_grid(r1 - r0);
-      double* part = ms->partial((size_t)grid * 2);
-      he_cross_kernel<<<grid, 256>>>(ms->m[i].indptr, ms->m[i].indices, ms->m[i].data, ms->m[j].indptr,
-                                     ms->m[j].indices, ms->m[j].data, r0, r1, part);
-      const int32_t dst[2] = {2 * K + i * K + j, 2 * K + K * K + i * K + j};
-      CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
-      reduce_partials_kernel<<<2, 256>>>(part, grid, 2, ms->d_dst, d_out);
-      g_launch_count += 2;
+  // pairs of different patterns: one fused pass per (group chunk, group chunk); chunks of <= 2 matrices
+  {
+    std::vector<std::vector<int>> chunks;
+    std::vector<char> seen(K, 0);
+    for (int k = 0; k < K; k++) {
+      if (seen[k]) continue;
+      std::vector<int> mem;
+      for (int t = k; t < K; t++)
+        if (!seen[t] && ms->m[t].pattern == ms->m[k].pattern) { mem.push_back(t); seen[t] = 1; }
+      for (size_t q = 0; q < mem.size(); q += 2)
+        chunks.push_back(std::vector<int>(mem.begin() + q, mem.begin() + std::min(mem.size(), q + 2)));
     }
+    for (size_t a = 0; a < chunks.size(); a++)
+      for (size_t b = 0; b < a; b++) {
+        if (ms->m[chunks[a][0]].pattern == ms->m[chunks[b][0]].pattern) {
+          // same pattern but different chunk (groups larger than the fused pass): fall back to pairwise kernel
+          for (int i : chunks[a]) for (int j : chunks[b]) {
+            const int grid = he_grid(r1 - r0);
+            double* part = ms->partial((size_t)grid * 2);
+            he_cross_kernel<<<grid, 256>>>(ms->m[i].indptr, ms->m[i].indices, ms->m[i].data, ms->m[j].indptr,
+                                           ms->m[j].indices, ms->m[j].data, r0, r1, part);
+            const int hi2 = std::max(i, j), lo2 = std::min(i, j);
+            const int32_t dst[2] = {2 * K + hi2 * K + lo2, 2 * K + K * K + hi2 * K + lo2};
+            CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
+            reduce_partials_kernel<<<2, 256>>>(part, grid, 2, ms->d_dst, d_out);
+            g_launch_count += 2;
+          }
+          continue;
+        }
+        // probe = the side with fewer nonzeros
+        const std::vector<int>& P = ms->m[chunks[a][0]].nnz <= ms->m[chunks[b][0]].nnz ? chunks[a] : chunks[b];
+        const std::vector<int>& T = (&P == &chunks[a]) ? chunks[b] : chunks[a];
+        const bool tpr = ms->m[P[0]].nnz < (int64_t)8 * ms->n;
+        const int gp = (int)P.size(), gt = (int)T.size(), nv = gp * gt * 2;
+        const int rows = r1 - r0;
+        const int grid = tpr ? std::max(1, std::min(148 * 8, (rows + 255) / 256)) : he_grid(rows);
+        double* part = ms->partial((size_t)grid * nv);
+        GroupArgs<2> pa, ta;
+        pa.indptr = ms->m[P[0]].indptr; pa.indices = ms->m[P[0]].indices;
+        ta.indptr = ms->m[T[0]].indptr; ta.indices = ms->m[T[0]].indices;
+        for (int q = 0; q < 2; q++) {
+          pa.data[q] = ms->m[P[std::min(q, gp - 1)]].data;
+          ta.data[q] = ms->m[T[std::min(q, gt - 1)]].data;
+        }
+        GroupArgs<1> p1, t1;
+        p1.indptr = pa.indptr; p1.indices = pa.indices; p1.data[0] = pa.data[0];
+        t1.indptr = ta.indptr; t1.indices = ta.indices; t1.data[0] = ta.data[0];
+#define CROSS(GP_, GT_, PA_, TA_)                                                                              \
+        if (tpr) he_cross_multi_kernel<GP_, GT_, true><<<grid, 256>>>(PA_, TA_, r0, r1, part);                     \
+        else he_cross_multi_kernel<GP_, GT_, false><<<grid, 256>>>(PA_, TA_, r0, r1, part);
+        if (gp == 1 && gt == 1) { CROSS(1, 1, p1, t1) }
+        else if (gp == 1 && gt == 2) { CROSS(1, 2, p1, ta) }
+        else if (gp == 2 && gt == 1) { CROSS(2, 1, pa, t1) }
+        else { CROSS(2, 2, pa, ta) }
+#undef CROSS
+        std::vector<int32_t> dst(nv);
+        for (int x = 0; x < gp; x++)
+          for (int z = 0; z < gt; z++) {
+            const int hi2 = std::max(P[x], T[z]), lo2 = std::min(P[x], T[z]);
+            dst[(x * gt + z) * 2] = 2 * K + hi2 * K + lo2;
+            dst[(x * gt + z) * 2 + 1] = 2 * K + K * K + hi2 * K + lo2;
+          }
+        CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst.data(), nv * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+        reduce_partials_kernel<<<nv, 256>>>(part, grid, nv, ms->d_dst, d_out);
+        g_launch_count += 2;
+      }
+  }
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
   SLMM_CATCH
