@@ -173,7 +173,7 @@ struct Launch {
 constexpr int BIG_STAGES = 4, SMALL_STAGES = 4;
 constexpr int BIG_SMEM = BIG_STAGES * 16 * (128 + 4) * 2 * 8 + 2 * BIG_STAGES * 8;
 constexpr int SMALL_SMEM = SMALL_STAGES * 16 * (64 + 4) * 2 * 8 + 2 * SMALL_STAGES * 8;
-constexpr int BIG_THREADS = 32 * (2 * 4 + 1), SMALL_THREADS = 32 * (2 * 2 + 1);
+constexpr int BIG_THREADS = 32 * (2 * 4 + NPW), SMALL_THREADS = 32 * (2 * 2 + NPW);
 
 struct Schedule {
   std::vector<Launch> launches;

@@ -84,14 +84,62 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
   }
 }
 
+constexpr int NPW = 4;   // producer warps (one warpgroup, so that setmaxnreg can hand its registers to the compute warps)
+
+template <int REGS>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+
+// One operand of one K slab -> shared memory, the share of producer warp `pw`.
+//   rows-major mode (unit or generic stride along the tile dimension): the warp copies k rows pw*4 .. pw*4+3 of the
+//     slab, 32 consecutive tile rows per LDGSTS (one coalesced 256-byte request when the stride is 1);
+//   k-contiguous mode: 16 consecutive k of 2 tile rows per LDGSTS; the warp copies tile rows [pw*T/4, (pw+1)*T/4).
+template <int T, int LD>
+__device__ __noinline__ void produce_operand(double* __restrict__ sm, const double* __restrict__ base, int64_t s_i,
+                                                int64_t s_k, const int32_t* __restrict__ kidx, bool kcontig, int rem,
+                                                int k0, int K, int pw, int lane) {
+  constexpr int KS = 16;
+  if (!kcontig) {
+    const int64_t lane_off = (int64_t)lane * s_i, chunk = 32 * s_i;
+#pragma unroll
+    for (int kq = 0; kq < KS / NPW; kq++) {
+      const int k = pw * (KS / NPW) + kq;
+      const bool kok = k0 + k < K;
+      int64_t gk = k0 + k;
+      if (kidx != nullptr) gk = kok ? kidx[k0 + k] : 0;
+      const double* src = base + gk * s_k + lane_off;
+      double* dst = sm + k * LD + lane;
+#pragma unroll
+      for (int c = 0; c < T / 32; c++) {
+        const bool ok = kok && (lane + 32 * c < rem);
+        cp_async8(dst + 32 * c, ok ? src + c * chunk : base, ok ? 8 : 0);
+      }
+    }
+  } else {
+    const int k = lane & 15, r = lane >> 4;
+    const bool kok = k0 + k < K;
+    const double* src = base + (k0 + k);
+    double* dst = sm + k * LD;
+#pragma unroll
+    for (int c = 0; c < T / 2 / NPW; c++) {
+      const int i = 2 * (pw * (T / 2 / NPW) + c) + r;
+      const bool ok = kok && i < rem;
+      cp_async8(dst + i, ok ? src + (int64_t)i * s_i : base, ok ? 8 : 0);
+    }
+  }
+}
+
 template <int TM, int TN, int NWM, int NWN, int STAGES>
-__global__ void __launch_bounds__(32 * (NWM * NWN + 1), 1) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
-  constexpr int NCW = NWM * NWN;           // compute warps
+__global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
+  constexpr int NCW = NWM * NWN;           // compute warps (a multiple of 4: whole warpgroups)
   constexpr int KS = 16;
   constexpr int WM = TM / NWM, WN = TN / NWN;
   constexpr int MI = WM / 8, NI = WN / 8;
   constexpr int LDA = TM + 4, LDB = TN + 4;
-  static_assert(TM % 32 == 0 && TN % 32 == 0, "producer mapping needs 32-row chunks");
+  // register rebalancing only where the compute warps need it (8 x 4 accumulator fragments per thread)
+  constexpr bool REBALANCE = (NCW == 8);
+  static_assert(TM % 32 == 0 && TN % 32 == 0 && NCW % 4 == 0, "producer mapping / warpgroup layout");
   extern __shared__ double smem[];
   double* As = smem;                           // [STAGES][KS][LDA]
   double* Bs = smem + STAGES * KS * LDA;       // [STAGES][KS][LDB]
@@ -116,13 +164,15 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + 1), 1) gemm_tiles_kernel(con
   const int M = op.M, N = op.N, K = op.K;
   const int nslab = (K + KS - 1) / KS;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 32); mbar_init(empty_bar + s, NCW); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 32 * NPW); mbar_init(empty_bar + s, NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == NCW) {
-    // ------------------------------------------------------------------ producer warp
+  if (warp >= NCW) {
+    // ------------------------------------------------------------------ producer warpgroup
+    if (REBALANCE) reg_dealloc<56>();
+    const int pw = warp - NCW;
     const int Mrem = M - tm0, Nrem = N - tn0;
     const int64_t a_si = op.a_si, a_sk = op.a_sk, b_sj = op.b_sj, b_sk = op.b_sk;
     const int32_t* kidx = op.a_kidx;
@@ -134,62 +184,13 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + 1), 1) gemm_tiles_kernel(con
       const int stage = s % STAGES, use = s / STAGES;
       if (use > 0) mbar_wait(empty_bar + stage, (use - 1) & 1);
       const int k0 = s * KS;
-      double* as = As + stage * KS * LDA;
-      double* bs = Bs + stage * KS * LDB;
-      if (!a_kcontig) {          // lanes along the rows of the tile: 32 consecutive rows per copy instruction
-        // gathered K index: one coalesced load of the slab's 16 row ids, broadcast by shuffle (a dependent
-        // scalar load per k would put ~16 memory latencies on the producer's critical path per slab)
-        int myk = 0;
-        if (kidx && lane < KS && k0 + lane < K) myk = kidx[k0 + lane];
-#pragma unroll 1
-        for (int k = 0; k < KS; k++) {
-          const bool kok = k0 + k < K;
-          const int gk = __shfl_sync(0xffffffffu, myk, k);
-          const int64_t kk = kidx ? (int64_t)gk : (int64_t)(k0 + k);
-          const double* src = Abase + kk * a_sk + (int64_t)lane * a_si;
-          double* dst = as + k * LDA + lane;
-#pragma unroll
-          for (int c = 0; c < TM / 32; c++) {
-            const bool ok = kok && (lane + 32 * c < Mrem);
-            cp_async8(dst + 32 * c, ok ? src + (int64_t)(32 * c) * a_si : Abase, ok ? 8 : 0);
-          }
-        }
-      } else {                   // k is the unit-stride dimension: 16 consecutive k of 2 rows per copy instruction
-        const int k = lane & 15, r = lane >> 4;
-        const bool kok = k0 + k < K;
-#pragma unroll 4
-        for (int c = 0; c < TM / 2; c++) {
-          const int i = 2 * c + r;
-          const bool ok = kok && i < Mrem;
-          cp_async8(as + k * LDA + i, ok ? Abase + (int64_t)i * a_si + (k0 + k) : Abase, ok ? 8 : 0);
-        }
-      }
-      if (!b_kcontig) {
-#pragma unroll 1
-        for (int k = 0; k < KS; k++) {
-          const bool kok = k0 + k < K;
-          const double* src = Bbase + (int64_t)(k0 + k) * b_sk + (int64_t)lane * b_sj;
-          double* dst = bs + k * LDB + lane;
-#pragma unroll
-          for (int c = 0; c < TN / 32; c++) {
-            const bool ok = kok && (lane + 32 * c < Nrem);
-            cp_async8(dst + 32 * c, ok ? src + (int64_t)(32 * c) * b_sj : Bbase, ok ? 8 : 0);
-          }
-        }
-      } else {
-        const int k = lane & 15, r = lane >> 4;
-        const bool kok = k0 + k < K;
-#pragma unroll 4
-        for (int c = 0; c < TN / 2; c++) {
-          const int j = 2 * c + r;
-          const bool ok = kok && j < Nrem;
-          cp_async8(bs + k * LDB + j, ok ? Bbase + (int64_t)j * b_sj + (k0 + k) : Bbase, ok ? 8 : 0);
-        }
-      }
+      produce_operand<TM, LDA>(As + stage * KS * LDA, Abase, a_si, a_sk, kidx, a_kcontig, Mrem, k0, K, pw, lane);
+      produce_operand<TN, LDB>(Bs + stage * KS * LDB, Bbase, b_sj, b_sk, nullptr, b_kcontig, Nrem, k0, K, pw, lane);
       mbar_cp_async_arrive(full_bar + stage);    // arrives (once per lane) when this lane's copies have landed
     }
     return;
   }
+  if (REBALANCE) reg_alloc<224>();
 
   // -------------------------------------------------------------------- compute warps
   const int g = lane >> 2, t = lane & 3;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + 1), 1) gemm_tiles_kernel(con
   const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG, lower = flags & GF_LOWER;
   double* Cb = op.C;
   const int64_t c_si = op.c_si, c_sj = op.c_sj;
-  constexpr int MB = 1;   // 9 warps share 4 register files of 16K: 168 registers per thread is the ceiling
+  constexpr int MB = 1;
 #pragma unroll
   for (int mb = 0; mb < MI; mb += MB) {
     double old[MB][NI][2];

@@ -14,6 +14,8 @@ chol = S.SparseCholesky(rng="device"); ses = chol._session(mats, cov, y); sig = 
 names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big"]
 def report(tag):
     ms, fl, kind, grid = ses.eng.launch_profile()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    np.savez(os.path.join(ROOT, "gpurun_out", "launches_%s.npz" % tag.split()[0]), ms=ms, fl=fl, kind=kind, grid=grid)
     print("==", tag, "launches", ms.size, "total %.1f ms" % ms.sum())
     for k in range(6):
         m = kind == k
