@@ -307,7 +307,8 @@ def main():
     t_solve = ev(lambda: ses.eng.solve_(Bs.clone())) - ev(lambda: Bs.clone())
     t_lmul = ev(lambda: ses.eng.lmul(Bs))
     Xq = torch.randn(n, s + 1, dtype=torch.float64, device="cuda")
-    t_quad = ev(lambda: [ses.matset.coldot(k, Xq) for k in range(K)])
+    groups = ses.matset.pattern_groups(2)
+    t_quad = ev(lambda: [ses.matset.quadform_multi(ks, Xq) for ks in groups])
     # profiled pass: per-kernel-kind device time with events around every launch
     assemble()
     ses.eng.set_profiling(True)
@@ -333,13 +334,18 @@ def main():
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
     nnzs = ses.matset.nnz
     solve_bytes = 2.0 * (8.0 * st["lsize"]) + 2 * 2 * 8.0 * n * s
-    quad_bytes = sum(12.0 * z + 4 * (n + 1) for z in nnzs[:1]) + 8.0 * nnzs[1] + 12.0 * nnzs[2] + K * 8.0 * n * (s + 1)
+    # symmetric half traversal: (4 + 8) bytes per visited entry of A, 8 more for AoA on the shared pattern, the
+    # gathered X rows are the real traffic (8 (s+1) bytes per visited entry, through L2) and are reported apart
+    half = [(z + n) / 2.0 for z in nnzs]
+    quad_bytes = 12.0 * half[0] + 4 * (n + 1) + 8.0 * half[1] + 12.0 * half[2] + 4 * (n + 1) + 2 * 8.0 * n * (s + 1)
+    quad_gather_bytes = (half[0] + half[2]) * 8.0 * (s + 1)
     phases = {
         "assemble_ms": round(t_asm, 3), "factorize_ms": round(t_fac, 2), "solve128_ms": round(t_solve, 2),
         "lmul128_ms": round(t_lmul, 2), "quadforms_ms": round(t_quad, 2),
         "cholesky_gflops": round(st["flops"] / t_fac / 1e6, 1),
         "cholesky_issued_gflops": round(st["issued_flops"] / t_fac / 1e6, 1),
         "solve_gbs": round(solve_bytes / t_solve / 1e6, 1), "quadforms_gbs": round(quad_bytes / t_quad / 1e6, 1),
+        "quadforms_gather_gbs": round(quad_gather_bytes / t_quad / 1e6, 1),
         "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src,
         "profile_ms": {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]},
     }

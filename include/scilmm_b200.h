@@ -76,6 +76,14 @@ int slmm_spmm_coldot(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t nc
  * (invV_C.T.dot(mats[i].dot(invV_C)), SparseCholesky.py:70).  ncols <= 160. */
 int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
                            int32_t store_from, double* d_store, int32_t row_begin, int32_t row_end, double* d_dots);
+/* Quadratic forms only (no stored product): d_dots[g*ncols + c] = x_c' A_ks[g] x_c over rows [row_begin,row_end).
+ * Symmetric matrices (checked once per matrix on the device, pattern and values) are traversed on and below the
+ * diagonal only, which halves the gathered-row traffic; others take the general pass.  Replaces
+ * np.sum(mats[i].dot(sim_vec) * sim_vec, axis=0) / invV_y.dot(mats[i].dot(invV_y)) (SparseCholesky.py:65-66). */
+int slmm_quadform_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
+                        int32_t row_begin, int32_t row_end, double* d_dots);
+/* *out = 1 when A_k equals its transpose bit for bit (device check, cached). */
+int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out);
 int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);
 
 /* ------------------------------------------------------------------ sparse Cholesky ------------------- */

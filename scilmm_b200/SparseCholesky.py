@@ -244,29 +244,22 @@ class RemlSession(object):
         comp1 = torch.zeros(K, dtype=torch.float64, device="cuda")
         comp2 = torch.zeros(K, dtype=torch.float64, device="cuda")
         gram = torch.zeros(K, c, c, dtype=torch.float64, device="cuda")
-        # one fused pass per pattern group over X = [W | V^-1 r | V^-1 C]: column quadratic forms for the probes and
-        # the residual, and A_k (V^-1 C) written out for the c x c REML trace term
+        # per pattern group: one pass for the column quadratic forms of X = [W | V^-1 r] (symmetric matrices are
+        # traversed on and below the diagonal only) and one narrow pass writing A_k (V^-1 C) for the c x c REML
+        # trace term
         s_loc = W.shape[1]
-        cols = [W, Vir.unsqueeze(1)] + ([ViC] if reml else [])
-        X = torch.cat(cols, dim=1).contiguous()
-        store_from = s_loc + 1 if reml else None
+        X = torch.cat([W, Vir.unsqueeze(1)], dim=1).contiguous()
         if self._groups is None:
             self._groups = self.matset.pattern_groups(2)
-        if X.shape[1] <= 160:
-            for ks in self._groups:
-                dots, stored = self.matset.coldot_multi(ks, X, store_from)
-                for g, k in enumerate(ks):
-                    comp1[k] = dots[g, :s_loc].sum()
-                    comp2[k] = dots[g, s_loc]
-                    if reml:
-                        gram[k] = ViC.t() @ stored[g]
-        else:
-            for k in range(K):
-                d = self.matset.coldot(k, X[:, :s_loc + 1].contiguous())
-                comp1[k] = d[:-1].sum()
-                comp2[k] = d[-1]
+        for ks in self._groups:
+            dots = self.matset.quadform_multi(ks, X)
+            if reml:
+                _, stored = self.matset.coldot_multi(ks, ViC, 0)
+            for g, k in enumerate(ks):
+                comp1[k] = dots[g, :s_loc].sum()
+                comp2[k] = dots[g, s_loc]
                 if reml:
-                    gram[k] = ViC.t() @ self.matset.spmm(k, ViC)
+                    gram[k] = ViC.t() @ stored[g]
         _shard.allreduce_sum_(comp1)                   # the only collective of an evaluation: K doubles
         comp1 = (comp1 / sim_num).cpu().numpy()
         comp2 = comp2.cpu().numpy()
@@ -332,7 +325,7 @@ def compute_gradients(sig2g_array, mats, sim_vec, invV_y, reml, invV_C, L_CT_inv
     ViC = _eng.to_device(np.asarray(invV_C, dtype=np.float64), torch)
     grad = np.zeros(len(sig2g_array))
     for k in range(len(sig2g_array)):
-        d = ms.coldot(k, X).cpu().numpy()
+        d = ms.quadform_multi([k], X)[0].cpu().numpy()
         grad[k] = 0.5 * (np.mean(d[:-1]) - d[-1])
         if reml:
             vec = (ViC.t() @ ms.spmm(k, ViC)).cpu().numpy()

@@ -216,18 +216,22 @@ struct PhaseBuilder {
   std::vector<PotrfOp> potrf;
   std::vector<ReduceOp> reduces;
   int64_t ws_used = 0;
-  void push(const GemmOp& op) {
-    if (op.M > 64 && op.N > 64) big.push_back(op); else small.push_back(op);
+  void push(const GemmOp& op, bool small_tiles) {
+    if (small_tiles) small.push_back(op); else big.push_back(op);
   }
   void add(GemmOp op) {
     if (op.M <= 0 || op.N <= 0 || op.K <= 0) return;
-    // Few output tiles but a long K (backward-solve gathers of fronts with few columns and many rows): split K
-    // across CTAs into workspace partials, reduced in fixed order by splitk_reduce_kernel.
-    const int T = (op.M > 64 && op.N > 64) ? 128 : 64;
-    const int64_t tiles = (int64_t)((op.M + T - 1) / T) * ((op.N + T - 1) / T);
-    if (!(op.flags & GF_LOWER) && tiles <= 148 && op.K >= 1024 && op.C != op.A) {
-      int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 256), std::max<int64_t>(2, 296 / tiles));
-      const int kc = (((op.K + S - 1) / S) + 15) / 16 * 16;
+    // Tile configuration: 128 x 128 tiles for large outputs; outputs that would leave most of the 148 SMs idle
+    // (the diagonal-block steps of the solves: nrhs x 512 with K = 512) take 64 x 64 tiles and, when K allows,
+    // split K across CTAs into workspace partials that splitk_reduce_kernel adds in fixed order.
+    const bool lower = op.flags & GF_LOWER;
+    const int64_t tb = (int64_t)((op.M + 127) / 128) * ((op.N + 127) / 128);
+    const int64_t ts = (int64_t)((op.M + 63) / 64) * ((op.N + 63) / 64);
+    const bool small_tiles = !(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128);
+    const int64_t tiles = small_tiles ? ts : tb;
+    if (!lower && tiles <= 148 && op.K >= 256 && op.C != op.A) {
+      int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 64), std::max<int64_t>(1, 148 / tiles));   // one wave of CTAs
+      const int kc = S > 0 ? (((op.K + S - 1) / S) + 15) / 16 * 16 : op.K;
       S = (op.K + kc - 1) / kc;
       if (S >= 2) {
         const int64_t mn = (int64_t)op.M * op.N;
@@ -246,13 +250,13 @@ struct PhaseBuilder {
           part.C = (double*)(intptr_t)(ws_used + (int64_t)c * mn);
           part.c_si = 1; part.c_sj = op.M;
           part.flags = GF_WS;
-          push(part);
+          push(part, small_tiles);
         }
         ws_used += (int64_t)S * mn;
         return;
       }
     }
-    push(op);
+    push(op, small_tiles);
   }
   void flush(Schedule& sch) {
     if (!potrf.empty()) {

@@ -22,6 +22,7 @@ struct CsrDev {
   bool owned_pattern = false, owned_data = false;
   std::vector<int32_t> h_indptr;   // kept for pattern comparison (uploaded matrices only)
   uint64_t idx_hash = 0;
+  int symmetric = -1;      // -1 unknown, 0 no, 1 yes (checked on the device on first use)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -431,6 +432,109 @@ __global__ void __launch_bounds__(256) spmm_group_kernel(const int32_t* __restri
   }
 }
 
+// Column quadratic forms x_c' A x_c for SYMMETRIC matrices sharing one pattern: only the entries on and below the
+// diagonal are visited (indices are sorted, so they are a prefix of every row), off-diagonal entries weighted
+// twice.  This halves the dominant traffic of the pass - the gathered rows of X, ncols*8 bytes per visited entry.
+//   dots[g][c] = sum_i x[i,c] * ( a_g(i,i) x[i,c] + 2 sum_{j<i} a_g(i,j) x[j,c] )
+// Replaces np.sum(mats[i].dot(sim_vec) * sim_vec, axis=0) and invV_y.dot(mats[i].dot(invV_y)),
+// reference scilmm/SparseCholesky.py:65-66 (same value up to summation order).
+template <int CPL, int G>
+__global__ void __launch_bounds__(256) quadform_sym_kernel(const int32_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ indices, GroupArgs<G> vals,
+                                                           const double* __restrict__ X, int ncols, int row_begin,
+                                                           int row_end, double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  double dot[G][CPL];
+#pragma unroll
+  for (int g = 0; g < G; g++)
+#pragma unroll
+    for (int c = 0; c < CPL; c++) dot[g][c] = 0.0;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    double acc[G][CPL];
+#pragma unroll
+    for (int g = 0; g < G; g++)
+#pragma unroll
+      for (int c = 0; c < CPL; c++) acc[g][c] = 0.0;
+    for (int p0 = b; p0 < e; p0 += 32) {
+      const int pl = p0 + lane;
+      const int mycol = pl < e ? __ldg(indices + pl) : 0x7fffffff;
+      const bool mine = mycol <= row;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, mine));   // sorted row: the lanes with col <= row are a prefix
+      double myval[G];
+      const double wgt = mycol == row ? 1.0 : 2.0;
+#pragma unroll
+      for (int g = 0; g < G; g++) myval[g] = mine ? wgt * __ldg(vals.data[g] + pl) : 0.0;
+      for (int k = 0; k < cnt; k++) {
+        const int col = __shfl_sync(0xffffffffu, mycol, k);
+        double v[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) v[g] = __shfl_sync(0xffffffffu, myval[g], k);
+        const double* xr = X + (int64_t)col * ncols;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+          const int j = lane + 32 * c;
+          if (j < ncols) {
+            const double x = xr[j];
+#pragma unroll
+            for (int g = 0; g < G; g++) acc[g][c] += v[g] * x;
+          }
+        }
+      }
+      if (cnt < 32) break;
+    }
+    const double* xi = X + (int64_t)row * ncols;
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const int j = lane + 32 * c;
+      if (j < ncols) {
+        const double x = xi[j];
+#pragma unroll
+        for (int g = 0; g < G; g++) dot[g][c] += acc[g][c] * x;
+      }
+    }
+  }
+  __shared__ double sh[8][32 * CPL];
+  for (int g = 0; g < G; g++) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CPL; c++) sh[warp][lane + 32 * c] = dot[g][c];
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncols; j += 256) {
+      double s2 = 0.0;
+      for (int w = 0; w < 8; w++) s2 += sh[w][j];
+      partial[((int64_t)blockIdx.x * G + g) * ncols + j] = s2;
+    }
+  }
+}
+
+// Symmetry check (pattern and values, bitwise): every stored (i,j), j > i, must have a stored (j,i) with the same
+// value.  flag is set to 1 on the first violation.
+__global__ void __launch_bounds__(256) symmetry_check_kernel(const int32_t* __restrict__ indptr,
+                                                             const int32_t* __restrict__ indices,
+                                                             const double* __restrict__ data, int n,
+                                                             int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    for (int p = b + lane; p < e; p += 32) {
+      const int col = indices[p];
+      if (col == row) continue;
+      bool okv = false;
+      if (col >= 0 && col < n) {
+        int lo = indptr[col], hi = indptr[col + 1];
+        const int end = hi;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (indices[mid] < row) lo = mid + 1; else hi = mid; }
+        okv = lo < end && indices[lo] == row &&
+              __double_as_longlong(data[lo]) == __double_as_longlong(data[p]);
+      }
+      if (!okv) *flag = 1;
+    }
+  }
+}
+
 }  // namespace slmm
 
 using namespace slmm;
@@ -781,6 +885,74 @@ int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, con
   if (cpl <= 1) { GROUP_CASE(1) } else if (cpl <= 2) { GROUP_CASE(2) } else if (cpl <= 3) { GROUP_CASE(3) }
   else if (cpl <= 4) { GROUP_CASE(4) } else { GROUP_CASE(5) }
 #undef GROUP_CASE
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out) {
+  SLMM_TRY
+  if (!ms || k < 0 || k >= ms->K || !out || !ms->m[k].data) throw std::invalid_argument("bad arguments");
+  CsrDev& c = ms->m[k];
+  if (c.symmetric < 0) {
+    int* d_flag = dev_alloc<int>(1);
+    CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
+    symmetry_check_kernel<<<he_grid(ms->n), 256>>>(c.indptr, c.indices, c.data, ms->n, d_flag);
+    g_launch_count++;
+    int flag = 1;
+    CUDA_OK(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    dev_free(d_flag);
+    c.symmetric = flag ? 0 : 1;
+  }
+  *out = c.symmetric;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+}  // extern "C"
+
+namespace slmm {
+template <int CPL, int G>
+static void launch_quadform_sym(slmm_matset* ms, const int32_t* ks, const double* d_X, int ncols, int r0, int r1,
+                                double* d_dots) {
+  GroupArgs<G> v;
+  v.indptr = ms->m[ks[0]].indptr;
+  v.indices = ms->m[ks[0]].indices;
+  for (int g = 0; g < G; g++) v.data[g] = ms->m[ks[g]].data;
+  const int grid = he_grid(r1 - r0);
+  double* part = ms->partial((size_t)grid * G * ncols);
+  quadform_sym_kernel<CPL, G><<<grid, 256>>>(v.indptr, v.indices, v, d_X, ncols, r0, r1, part);
+  reduce_partials_kernel<<<G * ncols, 256>>>(part, grid, G * ncols, nullptr, d_dots);
+  g_launch_count += 2;
+}
+}  // namespace slmm
+
+extern "C" {
+
+int slmm_quadform_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
+                        int32_t r0, int32_t r1, double* d_dots) {
+  SLMM_TRY
+  if (!ms || !ks || !d_X || !d_dots || nk <= 0 || nk > 2 || ncols <= 0 || ncols > 160)
+    throw std::invalid_argument("slmm_quadform_multi: need 1 <= nk <= 2, ncols <= 160");
+  if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
+  bool sym = true;
+  for (int g = 0; g < nk; g++) {
+    if (ks[g] < 0 || ks[g] >= ms->K || !ms->m[ks[g]].data) throw std::invalid_argument("matrix not set");
+    if (ms->m[ks[g]].pattern != ms->m[ks[0]].pattern) throw std::invalid_argument("matrices must share one pattern");
+    int32_t f = 0;
+    const int rc = slmm_matset_is_symmetric(ms, ks[g], &f);
+    if (rc != SLMM_OK) return rc;
+    sym = sym && f;
+  }
+  if (!sym)      // general matrices: full rows (no store columns)
+    return slmm_spmm_coldot_multi(ms, nk, ks, d_X, ncols, ncols, nullptr, r0, r1, d_dots);
+  const int cpl = (ncols + 31) / 32;
+#define QF_CASE(C)                                                                  \
+  if (nk == 1) launch_quadform_sym<C, 1>(ms, ks, d_X, ncols, r0, r1, d_dots);       \
+  else launch_quadform_sym<C, 2>(ms, ks, d_X, ncols, r0, r1, d_dots);
+  if (cpl <= 1) { QF_CASE(1) } else if (cpl <= 2) { QF_CASE(2) } else if (cpl <= 3) { QF_CASE(3) }
+  else if (cpl <= 4) { QF_CASE(4) } else { QF_CASE(5) }
+#undef QF_CASE
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
   SLMM_CATCH

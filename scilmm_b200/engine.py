@@ -237,6 +237,31 @@ class MatSet(object):
                                            int(row_end), dots.data_ptr()))
         return dots, store
 
+    def is_symmetric(self, k):
+        v = C.c_int32(0)
+        check(lib().slmm_matset_is_symmetric(self._h, int(k), C.byref(v)))
+        return bool(v.value)
+
+    def quadform_multi(self, ks, X, row_begin=0, row_end=None):
+        """dots[g, c] = X[:,c]' A_ks[g] X[:,c] for matrices `ks` sharing one pattern (symmetric matrices are
+        traversed on and below the diagonal only).  Any number of columns (processed 160 at a time)."""
+        torch = _torch()
+        X2 = (X if X.dim() == 2 else X.unsqueeze(1)).contiguous()
+        ncols = X2.shape[1]
+        row_end = self.n if row_end is None else row_end
+        ks_arr = np.asarray(ks, dtype=np.int32)
+        dots = torch.empty(len(ks), ncols, dtype=torch.float64, device="cuda")
+        for c0 in range(0, ncols, 160):
+            c1 = min(ncols, c0 + 160)
+            whole = c0 == 0 and c1 == ncols
+            blk = X2 if whole else X2[:, c0:c1].contiguous()
+            o = dots if whole else torch.empty(len(ks), c1 - c0, dtype=torch.float64, device="cuda")
+            check(lib().slmm_quadform_multi(self._h, len(ks), np_ptr(ks_arr), blk.data_ptr(), int(c1 - c0),
+                                            int(row_begin), int(row_end), o.data_ptr()))
+            if not whole:
+                dots[:, c0:c1] = o
+        return dots
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

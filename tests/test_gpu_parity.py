@@ -126,6 +126,32 @@ def test_spmm_and_coldot(golden_c1mini, eng):
                     assert rel_err(stored[gi].cpu().numpy(), ref[:, store_from:]) < 1e-13
 
 
+
+def test_quadform_symmetric_half_and_general_pass(golden_c1mini, eng):
+    """x' A x per column: symmetric matrices are traversed on/below the diagonal only, a non-symmetric matrix takes
+    the general pass; row shards add up (reference :65-66)."""
+    import scipy.sparse as sp
+    g = golden_c1mini
+    mats = g.mats("k3")
+    rng = np.random.default_rng(11)
+    N = sp.random(g.n, g.n, density=0.01, random_state=3, format="csr") + sp.eye(g.n).tocsr()   # not symmetric
+    ms = eng.MatSet(mats + [N.tocsr()])
+    assert ms.is_symmetric(0) and ms.is_symmetric(1) and ms.is_symmetric(2) and not ms.is_symmetric(3)
+    allm = mats + [N.tocsr()]
+    for ncols in (1, 2, 31, 97, 129, 160, 200):
+        X = rng.standard_normal((g.n, ncols))
+        Xd = eng.to_device(X)
+        for ks in ([0, 1], [2], [1], [3]):
+            dots = ms.quadform_multi(ks, Xd).cpu().numpy()
+            for gi, k in enumerate(ks):
+                assert rel_err(dots[gi], np.sum(allm[k].dot(X) * X, axis=0)) < 1e-12
+    X = rng.standard_normal((g.n, 40))
+    Xd = eng.to_device(X)
+    cut = g.n // 3
+    d = ms.quadform_multi([0, 1], Xd, 0, cut) + ms.quadform_multi([0, 1], Xd, cut, g.n) + \
+        ms.quadform_multi([0, 1], Xd, cut, cut)
+    assert rel_err(d.cpu().numpy()[0], np.sum(mats[0].dot(X) * X, axis=0)) < 1e-12
+
 # ------------------------------------------------------------------------------------------ factorization
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("tag", ["k2", "k4"])
