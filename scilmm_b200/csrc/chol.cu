@@ -28,7 +28,12 @@ int64_t g_launch_count = 0;
 
 constexpr int NBO = 512;   // outer block: columns updated together with K = NBO
 
-struct PullItem { int32_t p, c0, c1; };
+// One pull work item: target columns (rows, for RHS blocks) [c0,c1) of parent front p, and the range [e0,e1) of
+// PullEntry records listing exactly the children that contribute to it (a parent can have > 1000 children, most
+// of them touching only a few targets: walking all children per item was the dominant cost of the pulls).
+struct PullItem { int32_t p, c0, c1, e0, e1; };
+// rows [ta,tb) of the child's below-diagonal row list map into the item's target range
+struct PullEntry { int64_t rel_off, src_off; int32_t rsc, ta, tb, pad; };
 
 struct DevSym {
   const int32_t *sn_first, *sn_nrow, *rows, *rel, *child_ptr, *child_idx;
@@ -60,6 +65,7 @@ __device__ __forceinline__ int lower_bound_dev(const int32_t* a, int n, int v) {
 // distinct and the read-modify-write chains are independent.
 template <int TPI>
 __global__ void __launch_bounds__(TPI < 128 ? 128 : TPI) extend_add_kernel(const PullItem* __restrict__ items, int nitems,
+                                                                         const PullEntry* __restrict__ entries,
                                                                          DevSym S, double* __restrict__ Lx,
                                                                          const double* __restrict__ arena_child,
                                                                          double* __restrict__ arena_parent) {
@@ -71,14 +77,12 @@ __global__ void __launch_bounds__(TPI < 128 ? 128 : TPI) extend_add_kernel(const
   const int nsp = S.sn_first[p + 1] - S.sn_first[p], msp = S.sn_nrow[p], rsp = msp - nsp;
   double* panel = Lx + S.sn_lptr[p];
   double* Up = arena_parent + S.sn_uptr[p];
-  for (int q = S.child_ptr[p]; q < S.child_ptr[p + 1]; q++) {
-    const int c = S.child_idx[q];
-    const int nsc = S.sn_first[c + 1] - S.sn_first[c], rsc = S.sn_nrow[c] - nsc;
-    if (rsc == 0) continue;
-    const int32_t* __restrict__ relc = S.rel + S.sn_rowptr[c] + nsc;
-    const double* Uc = arena_child + S.sn_uptr[c];
-    const int ta = lower_bound_dev(relc, rsc, it.c0), tb = lower_bound_dev(relc, rsc, it.c1);
-    for (int tt = ta; tt < tb; tt++) {
+  for (int q = it.e0; q < it.e1; q++) {
+    const PullEntry en = entries[q];
+    const int rsc = en.rsc;
+    const int32_t* __restrict__ relc = S.rel + en.rel_off;
+    const double* Uc = arena_child + en.src_off;
+    for (int tt = en.ta; tt < en.tb; tt++) {
       const int pc = relc[tt];
       const double* __restrict__ src = Uc + (int64_t)tt * rsc;
       double* dst = pc < nsp ? panel + (int64_t)pc * msp : Up + (int64_t)(pc - nsp) * rsp - nsp;
@@ -96,23 +100,20 @@ __global__ void __launch_bounds__(TPI < 128 ? 128 : TPI) extend_add_kernel(const
 
 // Same pull for RHS blocks: target rows [c0,c1) of the parent front; rows < ns land in the permuted solution
 // block, the others in the parent's contribution block.  `sign` lets L*Z reuse it.
-__global__ void vec_pull_kernel(const PullItem* __restrict__ items, int nitems, DevSym S, double* __restrict__ X,
-                                const double* __restrict__ arena_child, double* __restrict__ arena_parent,
-                                const int64_t* __restrict__ vptr, int nrhs) {
+__global__ void vec_pull_kernel(const PullItem* __restrict__ items, int nitems, const PullEntry* __restrict__ entries,
+                                DevSym S, double* __restrict__ X, const double* __restrict__ arena_child,
+                                double* __restrict__ arena_parent, const int64_t* __restrict__ vptr, int nrhs) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= nitems) return;
   const PullItem it = items[w];
   const int p = it.p;
   const int fp = S.sn_first[p], nsp = S.sn_first[p + 1] - fp;
   double* Vp = arena_parent + vptr[p];
-  for (int q = S.child_ptr[p]; q < S.child_ptr[p + 1]; q++) {
-    const int c = S.child_idx[q];
-    const int nsc = S.sn_first[c + 1] - S.sn_first[c], rsc = S.sn_nrow[c] - nsc;
-    if (rsc == 0) continue;
-    const int32_t* relc = S.rel + S.sn_rowptr[c] + nsc;
-    const double* Vc = arena_child + vptr[c];
-    const int ta = lower_bound_dev(relc, rsc, it.c0), tb = lower_bound_dev(relc, rsc, it.c1);
-    for (int tt = ta; tt < tb; tt++) {
+  for (int q = it.e0; q < it.e1; q++) {
+    const PullEntry en = entries[q];
+    const int32_t* relc = S.rel + en.rel_off;
+    const double* Vc = arena_child + en.src_off;
+    for (int tt = en.ta; tt < en.tb; tt++) {
       const int pr = relc[tt];
       const double* src = Vc + (int64_t)tt * nrhs;
       double* dst = pr < nsp ? X + (int64_t)(fp + pr) * nrhs : Vp + (int64_t)(pr - nsp) * nrhs;
@@ -168,6 +169,7 @@ struct Launch {
   int32_t grid;     // CTAs
   int32_t child_parity;
   double flops;     // dense flops issued by this launch (0 for pulls)
+  int64_t tile_off; // GEMM launches: offset of this launch's tile -> op table
 };
 
 constexpr int BIG_STAGES = 4, SMALL_STAGES = 4;
@@ -180,7 +182,11 @@ struct Schedule {
   std::vector<GemmOp> gemm;
   std::vector<PotrfOp> potrf;
   std::vector<PullItem> pull;
+  std::vector<PullEntry> pull_entries;
+  PullEntry* d_pull_entries = nullptr;
   std::vector<ReduceOp> reduce;
+  std::vector<int32_t> tile_op;   // per GEMM launch: op index (relative to the launch's first op) of every tile
+  int32_t* d_tile_op = nullptr;
   int64_t ws_size = 0;            // doubles of split-K workspace (max over phases)
   double* d_ws = nullptr;
   ReduceOp* d_reduce = nullptr;
@@ -199,14 +205,17 @@ struct Schedule {
     d_gemm = dev_upload(gemm.data(), gemm.size());
     d_potrf = dev_upload(potrf.data(), potrf.size());
     d_pull = dev_upload(pull.data(), pull.size());
+    d_tile_op = dev_upload(tile_op.data(), tile_op.size());
+    d_pull_entries = dev_upload(pull_entries.data(), pull_entries.size());
   }
   void release() {
-    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_reduce);
+    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_reduce); dev_free(d_tile_op); dev_free(d_pull_entries);
+    d_tile_op = nullptr; d_pull_entries = nullptr;
     d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr; d_ws = nullptr; d_reduce = nullptr;
   }
   size_t device_bytes() const {
     return gemm.size() * sizeof(GemmOp) + potrf.size() * sizeof(PotrfOp) + pull.size() * sizeof(PullItem) +
-           reduce.size() * sizeof(ReduceOp) + (size_t)ws_size * 8;
+           reduce.size() * sizeof(ReduceOp) + (size_t)ws_size * 8 + tile_op.size() * 4 + pull_entries.size() * sizeof(PullEntry);
   }
 };
 
@@ -285,8 +294,13 @@ struct PhaseBuilder {
         lf += f;
       }
       if (tiles > 2000000000LL) throw std::runtime_error("too many tiles in one phase");
+      const int64_t tile_off = (int64_t)sch.tile_op.size();
+      sch.tile_op.resize(tile_off + tiles);
+      for (size_t q = 0; q < v.size(); q++)
+        std::fill(sch.tile_op.begin() + tile_off + v[q].tile_start,
+                  sch.tile_op.begin() + tile_off + v[q].tile_start + (int64_t)v[q].tiles_m * v[q].tiles_n, (int32_t)q);
       sch.launches.push_back({pass == 0 ? Launch::GEMM_BIG : Launch::GEMM_SMALL, (int64_t)sch.gemm.size(),
-                              (int32_t)v.size(), (int32_t)tiles, 0, lf});
+                              (int32_t)v.size(), (int32_t)tiles, 0, lf, tile_off});
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
     if (!reduces.empty()) {
@@ -388,21 +402,21 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM>>>(sch.d_potrf + L.off, h->d_info);
       break;
     case Launch::GEMM_BIG:
-      gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM>>>(sch.d_gemm + L.off, L.count);
+      gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
       break;
     case Launch::GEMM_SMALL:
-      gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM>>>(sch.d_gemm + L.off, L.count);
+      gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
       break;
     case Launch::PULL_MAT:
-      extend_add_kernel<32><<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, h->Lx,
+      extend_add_kernel<32><<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, h->Lx,
                                                         h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
       break;
     case Launch::PULL_MAT_BIG:
-      extend_add_kernel<256><<<L.count, 256>>>(sch.d_pull + L.off, L.count, ds, h->Lx, h->arena[L.child_parity],
+      extend_add_kernel<256><<<L.count, 256>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, h->Lx, h->arena[L.child_parity],
                                                h->arena[L.child_parity ^ 1]);
       break;
     case Launch::PULL_VEC:
-      vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, ds, X, vec_arena[L.child_parity],
+      vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, X, vec_arena[L.child_parity],
                                                   vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
       break;
     case Launch::REDUCE:
@@ -450,11 +464,13 @@ static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* c
   CUDA_OK(cudaGetLastError());
 }
 
-static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_kind, Launch::Kind kind, int chunk,
-                           int min_rows = 0, int max_rows = 1 << 30) {
+static void add_pull_items(Schedule& sch, const Symbolic& S, const std::vector<int64_t>& src_ptr, int level,
+                           int lo_kind, Launch::Kind kind, int chunk, int min_rows = 0, int max_rows = 1 << 30) {
   // lo_kind: 0 -> targets [0, ns)   1 -> targets [ns, ms)   2 -> targets [0, ms)
   // only parents with min_rows <= ms < max_rows are listed (lets the caller pick a kernel per size class)
+  // src_ptr[c]: offset of child c's update matrix / contribution block inside its level arena
   const int64_t off = (int64_t)sch.pull.size();
+  std::vector<std::vector<PullEntry>> per_item;
   for (int q = S.level_ptr[level]; q < S.level_ptr[level + 1]; q++) {
     const int p = S.level_sn[q];
     if (S.child_ptr[p + 1] == S.child_ptr[p]) continue;
@@ -462,11 +478,39 @@ static void add_pull_items(Schedule& sch, const Symbolic& S, int level, int lo_k
     if (ms < min_rows || ms >= max_rows) continue;
     const int a = lo_kind == 1 ? ns : 0, b = lo_kind == 0 ? ns : ms;
     // do not cross the ns boundary inside one item (the kernels branch on it per target)
+    std::vector<int> starts;
     for (int c0 = a; c0 < b;) {
       int c1 = std::min(b, c0 + chunk);
       if (c0 < ns && c1 > ns) c1 = ns;
-      sch.pull.push_back({p, c0, c1});
+      starts.push_back(c0);
       c0 = c1;
+    }
+    if (starts.empty()) continue;
+    starts.push_back(b);
+    const int nit = (int)starts.size() - 1;
+    per_item.assign(nit, std::vector<PullEntry>());
+    // children in fixed order; each child's sorted target list is cut at the item boundaries
+    for (int cq = S.child_ptr[p]; cq < S.child_ptr[p + 1]; cq++) {
+      const int c = S.child_idx[cq];
+      const int nsc = S.sn_first[c + 1] - S.sn_first[c], rsc = S.sn_nrow[c] - nsc;
+      if (rsc == 0) continue;
+      const int64_t rel_off = S.sn_rowptr[c] + nsc;
+      const int32_t* relc = S.rel.data() + rel_off;
+      int t = (int)(std::lower_bound(relc, relc + rsc, a) - relc);
+      int item = 0;
+      while (t < rsc && relc[t] < b) {
+        while (starts[item + 1] <= relc[t]) item++;
+        int tb = t;
+        while (tb < rsc && relc[tb] < starts[item + 1]) tb++;
+        per_item[item].push_back({rel_off, src_ptr[c], rsc, t, tb, 0});
+        t = tb;
+      }
+    }
+    for (int i = 0; i < nit; i++) {
+      if (per_item[i].empty()) continue;
+      const int32_t e0 = (int32_t)sch.pull_entries.size();
+      sch.pull_entries.insert(sch.pull_entries.end(), per_item[i].begin(), per_item[i].end());
+      sch.pull.push_back({p, starts[i], starts[i + 1], e0, (int32_t)sch.pull_entries.size()});
     }
   }
   const int cnt = (int)(sch.pull.size() - off);
@@ -500,8 +544,8 @@ static void build_factor_schedule(slmm_chol* h) {
   Schedule& sch = h->fact;
   PhaseBuilder pb;
   for (int d = S.nlevels - 1; d >= 0; d--) {
-    add_pull_items(sch, S, d, 0, Launch::PULL_MAT, 8, 0, 512);
-    add_pull_items(sch, S, d, 0, Launch::PULL_MAT_BIG, 4, 512);
+    add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT, 8, 0, 512);
+    add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT_BIG, 4, 512);
     int max_nib = 0;
     for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
       const int s = S.level_sn[q];
@@ -540,8 +584,8 @@ static void build_factor_schedule(slmm_chol* h) {
       }
       pb.flush(sch);
     }
-    add_pull_items(sch, S, d, 1, Launch::PULL_MAT, 8, 0, 512);
-    add_pull_items(sch, S, d, 1, Launch::PULL_MAT_BIG, 4, 512);
+    add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT, 8, 0, 512);
+    add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT_BIG, 4, 512);
   }
   // ---- batched triangular inversion of every NBO-wide diagonal block (all supernodes at once; off every front's
   //      critical path).  W = I, then forward substitution by NBI blocks:  W[t,:] = inv_t W[t,:];
@@ -609,7 +653,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
   // ---------------- forward:  L y = b  (levels deepest first).  X holds b and the running updates, the solved
   //                  blocks y land in X2 (out of place: Y = Winv * X per NBO-wide diagonal block).
   for (int d = S.nlevels - 1; d >= 0; d--) {
-    add_pull_items(pl->fwd, S, d, 0, Launch::PULL_VEC, 4);
+    add_pull_items(pl->fwd, S, vptr, d, 0, Launch::PULL_VEC, 4);
     int max_nob = 0;
     for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
       const int s = S.level_sn[q];
@@ -642,7 +686,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
       }
       pb.flush(pl->fwd);
     }
-    add_pull_items(pl->fwd, S, d, 1, Launch::PULL_VEC, 4);
+    add_pull_items(pl->fwd, S, vptr, d, 1, Launch::PULL_VEC, 4);
   }
   // ---------------- backward:  L' x = y  (roots first).  X2 holds y and the running updates, the solved blocks x
   //                  land in X; ancestors' final rows are read from X through the row lists.
@@ -694,7 +738,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
         pb.add(make_op(pl->arena[d & 1] + vptr[s], 1, R, pl->X + (int64_t)f * R, 1, R, P + ns, 1, ld, nrhs, rs, ns, 0));
     }
     pb.flush(pl->lmul);
-    add_pull_items(pl->lmul, S, d, 2, Launch::PULL_VEC, 4);
+    add_pull_items(pl->lmul, S, vptr, d, 2, Launch::PULL_VEC, 4);
   }
   pl->fwd.upload();
   pl->bwd.upload();

@@ -131,7 +131,8 @@ __device__ __noinline__ void produce_operand(double* __restrict__ sm, const doub
 }
 
 template <int TM, int TN, int NWM, int NWN, int STAGES>
-__global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(const GemmOp* __restrict__ ops, int nops) {
+__global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(const GemmOp* __restrict__ ops,
+                                                                                const int32_t* __restrict__ tile_op) {
   constexpr int NCW = NWM * NWN;           // compute warps (a multiple of 4: whole warpgroups)
   constexpr int KS = 16;
   constexpr int WM = TM / NWM, WN = TN / NWN;
@@ -146,14 +147,10 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(c
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(Bs + STAGES * KS * LDB);   // [STAGES]
   uint64_t* empty_bar = full_bar + STAGES;                                       // [STAGES]
 
-  // locate the operation this tile belongs to
-  int lo = 0, hi = nops - 1;
+  // the operation this tile belongs to: one table lookup (a binary search over tile_start costs ~15 dependent
+  // L2 round trips per CTA, which dominated launches made of thousands of tiny tiles)
   const int tile = blockIdx.x;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (ops[mid].tile_start <= tile) lo = mid; else hi = mid - 1;
-  }
-  const GemmOp& op = ops[lo];
+  const GemmOp& op = ops[tile_op[tile]];
   const int local = tile - op.tile_start;
   const int tiles_m = op.tiles_m;
   const int tm0 = (local % tiles_m) * TM, tn0 = (local / tiles_m) * TN;
