@@ -163,13 +163,15 @@ __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __re
 
 // ---------------------------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG, INIT_W, REDUCE } kind;
+  // EV_RECORD / EV_WAIT carry no kernel: `count` is an event id, recorded on / awaited by the launch's stream
+  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG, INIT_W, REDUCE, EV_RECORD, EV_WAIT } kind;
   int64_t off;      // offset into the matching op array
   int32_t count;    // ops / items
   int32_t grid;     // CTAs
   int32_t child_parity;
   double flops;     // dense flops issued by this launch (0 for pulls)
   int64_t tile_off; // GEMM launches: offset of this launch's tile -> op table
+  int32_t stream;   // 0: main (high priority) stream   1: bulk stream (look-ahead trailing updates)
 };
 
 constexpr int BIG_STAGES = 4, SMALL_STAGES = 4;
@@ -187,6 +189,7 @@ struct Schedule {
   std::vector<ReduceOp> reduce;
   std::vector<int32_t> tile_op;   // per GEMM launch: op index (relative to the launch's first op) of every tile
   int32_t* d_tile_op = nullptr;
+  int nevents = 0;                // events used by EV_RECORD / EV_WAIT
   int64_t ws_size = 0;            // doubles of split-K workspace (max over phases)
   double* d_ws = nullptr;
   ReduceOp* d_reduce = nullptr;
@@ -267,7 +270,8 @@ struct PhaseBuilder {
     }
     push(op, small_tiles);
   }
-  void flush(Schedule& sch) {
+  void flush(Schedule& sch, int stream = 0) {
+    const size_t first_launch = sch.launches.size();
     if (!potrf.empty()) {
       double pf = 0;
       for (const PotrfOp& o : potrf) pf += 2.0 * o.nb * o.nb * o.nb / 3.0;
@@ -313,9 +317,11 @@ struct PhaseBuilder {
       sch.reduce.insert(sch.reduce.end(), reduces.begin(), reduces.end());
       sch.ws_size = std::max(sch.ws_size, ws_used);
     }
+    for (size_t q = first_launch; q < sch.launches.size(); q++) sch.launches[q].stream = stream;
     big.clear(); small.clear(); potrf.clear(); reduces.clear();
     ws_used = 0;
   }
+  bool empty() const { return big.empty() && small.empty() && potrf.empty(); }
 };
 
 static GemmOp make_op(double* C, int64_t c_si, int64_t c_sj, const double* A, int64_t a_si, int64_t a_sk,
@@ -368,6 +374,9 @@ struct slmm_chol {
   Schedule fact;
   std::vector<EntryMap> maps;
   std::map<int, std::unique_ptr<SolvePlan>> plans;
+  cudaStream_t s_main = nullptr, s_bulk = nullptr;   // factorization streams (main: highest priority)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> events;
   bool factored = false;
   bool profiling = false;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -396,71 +405,106 @@ static void init_kernel_attributes() {
 }
 
 static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const DevSym& ds, double* X,
-                       double* const* vec_arena, const int64_t* d_vptr, int nrhs) {
+                       double* const* vec_arena, const int64_t* d_vptr, int nrhs, cudaStream_t st) {
   switch (L.kind) {
     case Launch::POTRF:
-      potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM>>>(sch.d_potrf + L.off, h->d_info);
+      potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM, st>>>(sch.d_potrf + L.off, h->d_info);
       break;
     case Launch::GEMM_BIG:
-      gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
+      gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM, st>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
       break;
     case Launch::GEMM_SMALL:
-      gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
+      gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM, st>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
       break;
     case Launch::PULL_MAT:
-      extend_add_kernel<32><<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, h->Lx,
-                                                        h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
+      extend_add_kernel<32><<<(L.count + 3) / 4, 128, 0, st>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, h->Lx,
+                                                               h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
       break;
     case Launch::PULL_MAT_BIG:
-      extend_add_kernel<256><<<L.count, 256>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, h->Lx, h->arena[L.child_parity],
-                                               h->arena[L.child_parity ^ 1]);
+      extend_add_kernel<256><<<L.count, 256, 0, st>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, h->Lx,
+                                                      h->arena[L.child_parity], h->arena[L.child_parity ^ 1]);
       break;
     case Launch::PULL_VEC:
-      vec_pull_kernel<<<(L.count + 3) / 4, 128>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, X, vec_arena[L.child_parity],
-                                                  vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
+      vec_pull_kernel<<<(L.count + 3) / 4, 128, 0, st>>>(sch.d_pull + L.off, L.count, sch.d_pull_entries, ds, X,
+                                                         vec_arena[L.child_parity], vec_arena[L.child_parity ^ 1], d_vptr, nrhs);
       break;
     case Launch::REDUCE:
-      splitk_reduce_kernel<<<L.grid, 256>>>(sch.d_reduce + L.off, L.count);
+      splitk_reduce_kernel<<<L.grid, 256, 0, st>>>(sch.d_reduce + L.off, L.count);
       break;
     case Launch::INIT_W:
-      init_identity_kernel<<<L.count, 256>>>(h->d_wblocks, h->W);
+      init_identity_kernel<<<L.count, 256, 0, st>>>(h->d_wblocks, h->W);
       break;
     default:
       break;
   }
 }
 
+static bool is_kernel(const Launch& L) { return L.kind != Launch::EV_RECORD && L.kind != Launch::EV_WAIT; }
+
+// Walks a launch list.  Single-stream schedules (solves, L*Z) run on the legacy default stream like every other
+// call of the library.  The factorization schedule names two streams: its critical chain (diagonal-block
+// factorizations, panel solves, next-panel updates) runs on a highest-priority stream, the look-ahead trailing
+// updates on a second one, ordered by events; both are forked from / joined to the default stream, so callers see
+// plain stream-0 semantics.  The list order is a valid topological order: the profiling mode simply runs it
+// serially on one stream with an event pair around every kernel.
 static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena, const int64_t* d_vptr,
                          int nrhs) {
   const DevSym ds = h->devsym();
+  int64_t nk = 0;
   if (!h->profiling) {
-    for (const Launch& L : sch.launches) launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs);
+    const bool two = sch.nevents > 0 && h->s_main != nullptr;
+    if (two) {
+      while ((int)h->events.size() < sch.nevents) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->events.push_back(e);
+      }
+      CUDA_OK(cudaEventRecord(h->ev_fork, 0));
+      CUDA_OK(cudaStreamWaitEvent(h->s_main, h->ev_fork, 0));
+      CUDA_OK(cudaStreamWaitEvent(h->s_bulk, h->ev_fork, 0));
+    }
+    for (const Launch& L : sch.launches) {
+      cudaStream_t st = two ? (L.stream ? h->s_bulk : h->s_main) : (cudaStream_t)0;
+      if (L.kind == Launch::EV_RECORD) { if (two) CUDA_OK(cudaEventRecord(h->events[L.count], st)); continue; }
+      if (L.kind == Launch::EV_WAIT) { if (two) CUDA_OK(cudaStreamWaitEvent(st, h->events[L.count], 0)); continue; }
+      launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs, st);
+      nk++;
+    }
+    if (two) {
+      CUDA_OK(cudaEventRecord(h->ev_join, h->s_bulk));
+      CUDA_OK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+      CUDA_OK(cudaEventRecord(h->ev_join, h->s_main));
+      CUDA_OK(cudaStreamWaitEvent(0, h->ev_join, 0));
+    }
   } else {
     // per-launch CUDA events on the launching stream (serialises nothing: same stream order), summed per kind
-    const size_t nl = sch.launches.size();
+    std::vector<const Launch*> ks;
+    for (const Launch& L : sch.launches) if (is_kernel(L)) ks.push_back(&L);
+    const size_t nl = ks.size();
     std::vector<cudaEvent_t> ev(nl + 1);
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
     CUDA_OK(cudaEventRecord(ev[0], 0));
     for (size_t i = 0; i < nl; i++) {
-      launch_one(h, sch, sch.launches[i], ds, X, vec_arena, d_vptr, nrhs);
+      launch_one(h, sch, *ks[i], ds, X, vec_arena, d_vptr, nrhs, 0);
       CUDA_OK(cudaEventRecord(ev[i + 1], 0));
     }
     CUDA_OK(cudaEventSynchronize(ev[nl]));
     for (size_t i = 0; i < nl; i++) {
       float ms = 0;
       CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-      const int k = (int)sch.launches[i].kind;
+      const int k = (int)ks[i]->kind;
       h->prof_ms[k] += ms;
-      h->prof_flops[k] += sch.launches[i].flops;
+      h->prof_flops[k] += ks[i]->flops;
       h->prof_n[k] += 1;
       h->prof_launch_ms.push_back(ms);
-      h->prof_launch_flops.push_back(sch.launches[i].flops);
+      h->prof_launch_flops.push_back(ks[i]->flops);
       h->prof_launch_kind.push_back(k);
-      h->prof_launch_grid.push_back(sch.launches[i].kind <= Launch::GEMM_SMALL ? sch.launches[i].grid : sch.launches[i].count);
+      h->prof_launch_grid.push_back(ks[i]->kind <= Launch::GEMM_SMALL ? ks[i]->grid : ks[i]->count);
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    nk = (int64_t)nl;
   }
-  g_launch_count += (int64_t)sch.launches.size();
+  g_launch_count += nk;
   CUDA_OK(cudaGetLastError());
 }
 
@@ -542,7 +586,8 @@ static OuterBlock outer_block(const slmm_chol* h, int s, int ob) {
 static void build_factor_schedule(slmm_chol* h) {
   const Symbolic& S = h->S;
   Schedule& sch = h->fact;
-  PhaseBuilder pb;
+  PhaseBuilder pb, pb_rest;
+  int last_bulk_ev = -1;
   for (int d = S.nlevels - 1; d >= 0; d--) {
     add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT, 8, 0, 512);
     add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT_BIG, 4, 512);
@@ -553,6 +598,7 @@ static void build_factor_schedule(slmm_chol* h) {
     }
     for (int ph = 0; ph < 3 * max_nib; ph++) {
       const int ib = ph / 3, kind = ph % 3;
+      bool outer_done = false;
       for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
         const int s = S.level_sn[q];
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
@@ -574,15 +620,45 @@ static void build_factor_schedule(slmm_chol* h) {
             pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, ms - c1,
                            ob_end - c1, nb, GF_LOWER | GF_ACCUM | GF_NEG));
           } else if (c1 < ns) {       // outer block finished: update all remaining panel columns, K = block width
+            // Look-ahead: the columns of the NEXT outer block are updated on the main stream (they gate the next
+            // panel factorization); the columns beyond it go to the bulk stream and overlap with that panel
+            // factorization, whose diagonal-block steps leave almost every SM idle.
+            outer_done = true;
+            const int nx = std::min(ns, c1 + NBO);
+            const bool split = (ns - nx) >= NBO;
+            const int ncols = split ? nx - c1 : ns - c1;
             pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, ms - c1,
-                           ns - c1, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
+                           ncols, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
+            if (split)
+              pb_rest.add(make_op(P + nx + nx * ld, 1, ld, P + nx + ob0 * ld, 1, ld, P + nx + ob0 * ld, 1, ld, ms - nx,
+                                  ns - nx, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
           } else if (rs > 0) {        // panel done: Schur complement  U = -L21 L21'
             double* U = h->arena[d & 1] + h->uptr[s];
             pb.add(make_op(U, 1, rs, P + ns, 1, ld, P + ns, 1, ld, rs, rs, ns, GF_LOWER | GF_NEG));
           }
         }
       }
-      pb.flush(sch);
+      if (pb_rest.empty()) {
+        // an unsplit trailing update still writes columns the previous bulk update may be writing
+        if (outer_done && last_bulk_ev >= 0) {
+          sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
+          last_bulk_ev = -1;
+        }
+        pb.flush(sch);
+      } else {
+        const int ev_panel = sch.nevents++, ev_rest = sch.nevents++;
+        sch.launches.push_back({Launch::EV_RECORD, 0, ev_panel, 0, 0, 0.0, 0, 0});    // panels of this block are final
+        if (last_bulk_ev >= 0) sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
+        pb.flush(sch, 0);                                                             // next-panel updates (+ other fronts)
+        sch.launches.push_back({Launch::EV_WAIT, 0, ev_panel, 0, 0, 0.0, 0, 1});
+        pb_rest.flush(sch, 1);
+        sch.launches.push_back({Launch::EV_RECORD, 0, ev_rest, 0, 0, 0.0, 0, 1});
+        last_bulk_ev = ev_rest;
+      }
+    }
+    if (last_bulk_ev >= 0) {        // level boundary: everything of this level is complete before the pulls
+      sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
+      last_bulk_ev = -1;
     }
     add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT, 8, 0, 512);
     add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT_BIG, 4, 512);
@@ -825,6 +901,14 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
   h->arena[1] = dev_alloc<double>(h->arena_size[1]);
   h->d_info = dev_alloc<int>(1);
   h->d_partial = dev_alloc<double>(1024);
+  {
+    int least = 0, greatest = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_OK(cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, greatest));
+    CUDA_OK(cudaStreamCreateWithPriority(&h->s_bulk, cudaStreamNonBlocking, least));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   CUDA_OK(cudaMemset(h->Lx, 0, S.lsize * sizeof(double)));
   build_factor_schedule(h.get());
   h->bytes = (S.lsize + h->invptr[S.nsuper] + h->wptr[S.nsuper] + h->arena_size[0] + h->arena_size[1]) * 8 +
@@ -842,6 +926,11 @@ int slmm_chol_destroy(slmm_chol_t* h) {
   dev_free(h->d_sn_rowptr); dev_free(h->d_sn_lptr); dev_free(h->d_sn_uptr);
   dev_free(h->Lx); dev_free(h->inv); dev_free(h->W); dev_free(h->d_wblocks); dev_free(h->arena[0]); dev_free(h->arena[1]);
   dev_free(h->d_info); dev_free(h->d_partial);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->s_main) cudaStreamDestroy(h->s_main);
+  if (h->s_bulk) cudaStreamDestroy(h->s_bulk);
   h->fact.release();
   for (auto& m : h->maps) dev_free(m.d_map);
   for (auto& kv : h->plans) kv.second->release();

@@ -230,6 +230,36 @@ def test_wide_supernodes_and_many_rhs(slmm, eng):
         assert rel_err(X, np.linalg.solve(V.toarray(), Bm)) < 1e-10
 
 
+def test_lookahead_streams_dense_front(slmm, eng):
+    """A 2300-column dense front with rows below it: outer blocks 0..4, so the trailing updates are split between the
+    main and the bulk stream (look-ahead).  Factor twice and compare bit for bit (no races, fixed summation
+    order), then check logdet / solve against LAPACK."""
+    rng = np.random.default_rng(5)
+    nd, nt = 2300, 400
+    B = rng.standard_normal((nd, nd))
+    D = B @ B.T / nd + 2.0 * np.eye(nd)
+    T = sp.random(nt, nt, 0.02, random_state=1)
+    T = (T + T.T + 20 * sp.eye(nt)).toarray()
+    V = np.zeros((nd + nt, nd + nt))
+    V[nt:, nt:] = D
+    V[:nt, :nt] = T
+    C = 0.01 * rng.standard_normal((nd, 60))
+    V[nt:, :60] = C
+    V[:60, nt:] = C.T
+    Vs = sp.csc_matrix(V)
+    chol = slmm.SparseCholesky(ordering_method="natural")
+    f = chol(Vs)
+    L1 = f.L().toarray()
+    f = chol(Vs)
+    L2 = f.L().toarray()
+    assert np.array_equal(L1, L2)
+    sign, ld = np.linalg.slogdet(V)
+    assert abs(f.logdet() - ld) < 1e-10 * abs(ld)
+    Bm = rng.standard_normal((nd + nt, 7))
+    assert rel_err(f(Bm), np.linalg.solve(V, Bm)) < 1e-10
+    assert rel_err(L2 @ L2.T, V) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------ REML
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("tag", ["k2", "k4"])
