@@ -82,6 +82,13 @@ int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, con
  * np.sum(mats[i].dot(sim_vec) * sim_vec, axis=0) / invV_y.dot(mats[i].dot(invV_y)) (SparseCholesky.py:65-66). */
 int slmm_quadform_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
                         int32_t row_begin, int32_t row_end, double* d_dots);
+/* Same pass with a narrow block riding along: XB is n x nb (nb <= 16), C-ordered, typically [V^-1 C | V^-1 y].
+ * d_gram_half[g][nb][nb] receives Mh with XB' A_ks[g] XB = Mh + Mh' - every c x c quantity of the REML gradient
+ * (invV_C.T.dot(mats[i].dot(invV_C)), SparseCholesky.py:70, and by linearity invV_y.dot(mats[i].dot(invV_y)), :66)
+ * without a second pass over the matrix.  Symmetric matrices only. */
+int slmm_quadform_gram_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
+                             const double* d_XB, int32_t nb, int32_t row_begin, int32_t row_end, double* d_dots,
+                             double* d_gram_half);
 /* *out = 1 when A_k equals its transpose bit for bit (device check, cached). */
 int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out);
 int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);

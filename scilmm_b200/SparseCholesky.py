@@ -193,6 +193,7 @@ class RemlSession(object):
         c = self.C.shape[1]
         B = torch.cat([self.C, self.y.unsqueeze(1)], dim=1).contiguous()
         self.eng.solve_(B)
+        self._ViCy = B                                  # [V^-1 C | V^-1 y], kept for the fused Gram pass
         ViC = B[:, :c].contiguous()
         Viy = B[:, c].contiguous()
         CtViC = (self.C.t() @ ViC).cpu().numpy()
@@ -244,22 +245,33 @@ class RemlSession(object):
         comp1 = torch.zeros(K, dtype=torch.float64, device="cuda")
         comp2 = torch.zeros(K, dtype=torch.float64, device="cuda")
         gram = torch.zeros(K, c, c, dtype=torch.float64, device="cuda")
-        # per pattern group: one pass for the column quadratic forms of X = [W | V^-1 r] (symmetric matrices are
-        # traversed on and below the diagonal only) and one narrow pass writing A_k (V^-1 C) for the c x c REML
-        # trace term
+        # Per pattern group ONE pass over the matrices: column quadratic forms of the probes W (symmetric matrices
+        # are traversed on/below the diagonal only) and, riding along, the Gram matrix of the narrow block
+        # B = [V^-1 C | V^-1 r]: its last diagonal entry is r'V^-1 A_k V^-1 r (:66), its leading c x c block feeds
+        # the REML trace term (:70).
         s_loc = W.shape[1]
-        X = torch.cat([W, Vir.unsqueeze(1)], dim=1).contiguous()
         if self._groups is None:
             self._groups = self.matset.pattern_groups(2)
+            self._sym = [self.matset.is_symmetric(k) for k in range(K)]
+        Bq = self._ViCy
+        Bq[:, c] = Vir                                 # Viy was copied out above; the block becomes [V^-1 C | V^-1 r]
         for ks in self._groups:
-            dots = self.matset.quadform_multi(ks, X)
-            if reml:
-                _, stored = self.matset.coldot_multi(ks, ViC, 0)
-            for g, k in enumerate(ks):
-                comp1[k] = dots[g, :s_loc].sum()
-                comp2[k] = dots[g, s_loc]
+            if all(self._sym[k] for k in ks) and Bq.shape[1] <= 16 and s_loc <= 160:
+                dots, G = self.matset.quadform_gram_multi(ks, W, Bq)
+                for g, k in enumerate(ks):
+                    comp1[k] = dots[g].sum()
+                    comp2[k] = G[g][c, c]
+                    gram[k] = G[g][:c, :c]
+            else:                                      # general matrices / very wide blocks: separate passes
+                X = torch.cat([W, Vir.unsqueeze(1)], dim=1).contiguous()
+                dots = self.matset.quadform_multi(ks, X)
                 if reml:
-                    gram[k] = ViC.t() @ stored[g]
+                    _, stored = self.matset.coldot_multi(ks, ViC, 0)
+                for g, k in enumerate(ks):
+                    comp1[k] = dots[g, :s_loc].sum()
+                    comp2[k] = dots[g, s_loc]
+                    if reml:
+                        gram[k] = ViC.t() @ stored[g]
         _shard.allreduce_sum_(comp1)                   # the only collective of an evaluation: K doubles
         comp1 = (comp1 / sim_num).cpu().numpy()
         comp2 = comp2.cpu().numpy()

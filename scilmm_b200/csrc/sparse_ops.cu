@@ -438,6 +438,8 @@ __global__ void __launch_bounds__(256) spmm_group_kernel(const int32_t* __restri
 //   dots[g][c] = sum_i x[i,c] * ( a_g(i,i) x[i,c] + 2 sum_{j<i} a_g(i,j) x[j,c] )
 // Replaces np.sum(mats[i].dot(sim_vec) * sim_vec, axis=0) and invV_y.dot(mats[i].dot(invV_y)),
 // reference scilmm/SparseCholesky.py:65-66 (same value up to summation order).
+constexpr int QF_NB = 16;   // widest narrow block [V^-1 C | V^-1 r] the Gram pass takes
+
 template <int CPL, int G>
 __global__ void __launch_bounds__(256) quadform_sym_kernel(const int32_t* __restrict__ indptr,
                                                            const int32_t* __restrict__ indices, GroupArgs<G> vals,
@@ -506,6 +508,76 @@ __global__ void __launch_bounds__(256) quadform_sym_kernel(const int32_t* __rest
       for (int w = 0; w < 8; w++) s2 += sh[w][j];
       partial[((int64_t)blockIdx.x * G + g) * ncols + j] = s2;
     }
+  }
+}
+
+// Gram matrix XB' A XB of a NARROW block (n x nb, nb <= 16, e.g. [V^-1 C | V^-1 r]) for symmetric matrices sharing
+// one pattern, again on/below the diagonal only:
+//   hb_i = a(i,i)/2 xb_i + sum_{j<i} a(i,j) xb_j,   Mh = sum_i xb_i hb_i',   XB' A XB = Mh + Mh'.
+// A warp owns a row and works on two entries at a time: lane = (half, j), half = which entry, j = column of XB.
+// Lane (half, j) accumulates Mh[8*half + a][j], a = 0..7, over all rows of the warp.
+// Replaces invV_C.T.dot(mats[i].dot(invV_C)) and invV_y.dot(mats[i].dot(invV_y)), reference :66,:70.
+template <int G>
+__global__ void __launch_bounds__(256) gram_sym_kernel(const int32_t* __restrict__ indptr,
+                                                       const int32_t* __restrict__ indices, GroupArgs<G> vals,
+                                                       const double* __restrict__ XB, int nb, int row_begin,
+                                                       int row_end, double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, j = lane & 15;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  double mh[G][8];
+#pragma unroll
+  for (int g = 0; g < G; g++)
+#pragma unroll
+    for (int a = 0; a < 8; a++) mh[g][a] = 0.0;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    double hb[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) hb[g] = 0.0;
+    for (int p0 = b; p0 < e; p0 += 32) {
+      const int pl = p0 + lane;
+      const int mycol = pl < e ? __ldg(indices + pl) : 0x7fffffff;
+      const bool mine = mycol <= row;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, mine));
+      double myval[G];
+      const double wgt = mycol == row ? 0.5 : 1.0;
+#pragma unroll
+      for (int g = 0; g < G; g++) myval[g] = mine ? wgt * __ldg(vals.data[g] + pl) : 0.0;
+#pragma unroll 4
+      for (int k = 0; k < cnt; k += 2) {
+        const int src = min(k + half, 31);
+        const int col = __shfl_sync(0xffffffffu, mycol, src);
+        double v[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) v[g] = __shfl_sync(0xffffffffu, myval[g], src);   // 0 for entries past the prefix
+        const double x = (j < nb && col <= row) ? XB[(int64_t)col * nb + j] : 0.0;
+#pragma unroll
+        for (int g = 0; g < G; g++) hb[g] += v[g] * x;
+      }
+      if (cnt < 32) break;
+    }
+    const double xbi = j < nb ? XB[(int64_t)row * nb + j] : 0.0;
+#pragma unroll
+    for (int g = 0; g < G; g++) hb[g] += __shfl_xor_sync(0xffffffffu, hb[g], 16);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const double xa = __shfl_sync(0xffffffffu, xbi, 8 * half + a);
+#pragma unroll
+      for (int g = 0; g < G; g++) mh[g][a] += xa * hb[g];
+    }
+  }
+  __shared__ double sh[8][G][QF_NB][QF_NB];    // [warp][g][a][j]
+#pragma unroll
+  for (int g = 0; g < G; g++)
+#pragma unroll
+    for (int a = 0; a < 8; a++) sh[warp][g][8 * half + a][j] = mh[g][a];
+  __syncthreads();
+  for (int q = threadIdx.x; q < G * nb * nb; q += 256) {
+    const int g = q / (nb * nb), a = (q / nb) % nb, jj = q % nb;
+    double s2 = 0.0;
+    for (int w = 0; w < 8; w++) s2 += sh[w][g][a][jj];
+    partial[(int64_t)blockIdx.x * G * nb * nb + q] = s2;
   }
 }
 
@@ -913,17 +985,23 @@ int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out) {
 
 namespace slmm {
 template <int CPL, int G>
-static void launch_quadform_sym(slmm_matset* ms, const int32_t* ks, const double* d_X, int ncols, int r0, int r1,
-                                double* d_dots) {
+static void launch_quadform_sym(slmm_matset* ms, const int32_t* ks, const double* d_X, int ncols, const double* d_XB,
+                                int nb, int r0, int r1, double* d_dots, double* d_gram) {
   GroupArgs<G> v;
   v.indptr = ms->m[ks[0]].indptr;
   v.indices = ms->m[ks[0]].indices;
   for (int g = 0; g < G; g++) v.data[g] = ms->m[ks[g]].data;
   const int grid = he_grid(r1 - r0);
-  double* part = ms->partial((size_t)grid * G * ncols);
+  const size_t np = (size_t)grid * G * ncols, ng = d_XB ? (size_t)grid * G * nb * nb : 0;
+  double* part = ms->partial(np + ng);
   quadform_sym_kernel<CPL, G><<<grid, 256>>>(v.indptr, v.indices, v, d_X, ncols, r0, r1, part);
   reduce_partials_kernel<<<G * ncols, 256>>>(part, grid, G * ncols, nullptr, d_dots);
   g_launch_count += 2;
+  if (d_XB) {
+    gram_sym_kernel<G><<<grid, 256>>>(v.indptr, v.indices, v, d_XB, nb, r0, r1, part + np);
+    reduce_partials_kernel<<<G * nb * nb, 256>>>(part + np, grid, G * nb * nb, nullptr, d_gram);
+    g_launch_count += 2;
+  }
 }
 }  // namespace slmm
 
@@ -931,9 +1009,16 @@ extern "C" {
 
 int slmm_quadform_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
                         int32_t r0, int32_t r1, double* d_dots) {
+  return slmm_quadform_gram_multi(ms, nk, ks, d_X, ncols, nullptr, 0, r0, r1, d_dots, nullptr);
+}
+
+int slmm_quadform_gram_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
+                             const double* d_XB, int32_t nb, int32_t r0, int32_t r1, double* d_dots,
+                             double* d_gram_half) {
   SLMM_TRY
   if (!ms || !ks || !d_X || !d_dots || nk <= 0 || nk > 2 || ncols <= 0 || ncols > 160)
-    throw std::invalid_argument("slmm_quadform_multi: need 1 <= nk <= 2, ncols <= 160");
+    throw std::invalid_argument("slmm_quadform_gram_multi: need 1 <= nk <= 2, ncols <= 160");
+  if (d_XB && (nb <= 0 || nb > QF_NB || !d_gram_half)) throw std::invalid_argument("narrow block: 1 <= nb <= 16");
   if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
   bool sym = true;
   for (int g = 0; g < nk; g++) {
@@ -944,12 +1029,14 @@ int slmm_quadform_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
     if (rc != SLMM_OK) return rc;
     sym = sym && f;
   }
-  if (!sym)      // general matrices: full rows (no store columns)
-    return slmm_spmm_coldot_multi(ms, nk, ks, d_X, ncols, ncols, nullptr, r0, r1, d_dots);
+  if (!sym) {
+    if (d_XB) throw std::invalid_argument("the fused Gram path needs symmetric matrices (use slmm_spmm_coldot_multi)");
+    return slmm_spmm_coldot_multi(ms, nk, ks, d_X, ncols, ncols, nullptr, r0, r1, d_dots);   // full rows
+  }
   const int cpl = (ncols + 31) / 32;
-#define QF_CASE(C)                                                                  \
-  if (nk == 1) launch_quadform_sym<C, 1>(ms, ks, d_X, ncols, r0, r1, d_dots);       \
-  else launch_quadform_sym<C, 2>(ms, ks, d_X, ncols, r0, r1, d_dots);
+#define QF_CASE(C)                                                                                   \
+  if (nk == 1) launch_quadform_sym<C, 1>(ms, ks, d_X, ncols, d_XB, nb, r0, r1, d_dots, d_gram_half); \
+  else launch_quadform_sym<C, 2>(ms, ks, d_X, ncols, d_XB, nb, r0, r1, d_dots, d_gram_half);
   if (cpl <= 1) { QF_CASE(1) } else if (cpl <= 2) { QF_CASE(2) } else if (cpl <= 3) { QF_CASE(3) }
   else if (cpl <= 4) { QF_CASE(4) } else { QF_CASE(5) }
 #undef QF_CASE

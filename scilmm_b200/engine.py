@@ -237,6 +237,21 @@ class MatSet(object):
                                            int(row_end), dots.data_ptr()))
         return dots, store
 
+    def quadform_gram_multi(self, ks, X, XB, row_begin=0, row_end=None):
+        """One pass over symmetric matrices `ks` (one pattern): (dots[g, c] = X[:,c]' A X[:,c],
+        gram[g] = XB' A XB) for a wide block X (<= 160 columns) and a narrow one XB (<= 16 columns)."""
+        torch = _torch()
+        X2, B2 = X.contiguous(), XB.contiguous()
+        ncols, nb = X2.shape[1], B2.shape[1]
+        row_end = self.n if row_end is None else row_end
+        ks_arr = np.asarray(ks, dtype=np.int32)
+        dots = torch.empty(len(ks), ncols, dtype=torch.float64, device="cuda")
+        half = torch.empty(len(ks), nb, nb, dtype=torch.float64, device="cuda")
+        check(lib().slmm_quadform_gram_multi(self._h, len(ks), np_ptr(ks_arr), X2.data_ptr(), int(ncols),
+                                             B2.data_ptr(), int(nb), int(row_begin), int(row_end),
+                                             dots.data_ptr(), half.data_ptr()))
+        return dots, half + half.transpose(1, 2)
+
     def is_symmetric(self, k):
         v = C.c_int32(0)
         check(lib().slmm_matset_is_symmetric(self._h, int(k), C.byref(v)))

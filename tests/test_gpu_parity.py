@@ -145,6 +145,14 @@ def test_quadform_symmetric_half_and_general_pass(golden_c1mini, eng):
             dots = ms.quadform_multi(ks, Xd).cpu().numpy()
             for gi, k in enumerate(ks):
                 assert rel_err(dots[gi], np.sum(allm[k].dot(X) * X, axis=0)) < 1e-12
+    # fused pass: wide block + narrow block whose Gram matrix rides along
+    for ncols, nb in ((128, 12), (20, 1), (100, 16), (33, 5)):
+        X, XB = rng.standard_normal((g.n, ncols)), rng.standard_normal((g.n, nb))
+        for ks in ([0, 1], [2]):
+            dots, G = ms.quadform_gram_multi(ks, eng.to_device(X), eng.to_device(XB))
+            for gi, k in enumerate(ks):
+                assert rel_err(dots[gi].cpu().numpy(), np.sum(allm[k].dot(X) * X, axis=0)) < 1e-12
+                assert rel_err(G[gi].cpu().numpy(), XB.T.dot(allm[k].dot(XB))) < 1e-12
     X = rng.standard_normal((g.n, 40))
     Xd = eng.to_device(X)
     cut = g.n // 3
