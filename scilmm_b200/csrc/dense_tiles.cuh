@@ -177,6 +177,19 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(c
     const bool b_kcontig = (b_sk == 1 && b_sj != 1);
     const double* Abase = op.A + (int64_t)tm0 * a_si;
     const double* Bbase = op.B + (int64_t)tn0 * b_sj;
+    // Accumulating tiles read C in the epilogue: pull the tile into L2 now, under the main loop, so that the
+    // epilogue's dependent loads cost an L2 hit instead of a DRAM round trip (one CTA per SM: nothing else would
+    // hide them).  Column-major C only (unit row stride): one 128-byte line per 16 rows.
+    if ((flags & GF_ACCUM) && op.c_si == 1) {
+      const int pt = pw * 32 + lane;                       // 0..127: one tile column per producer thread
+      if (pt < TN && tn0 + pt < N) {
+        const double* ccol = op.C + (int64_t)tm0 + (int64_t)(tn0 + pt) * op.c_sj;
+        const int rows = min(TM, M - tm0);
+        const int r_first = (flags & GF_LOWER) ? max(0, tn0 + pt - tm0) : 0;
+        for (int r = (r_first / 16) * 16; r < rows; r += 16)
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ccol + r));
+      }
+    }
     for (int s = 0; s < nslab; s++) {
       const int stage = s % STAGES, use = s / STAGES;
       if (use > 0) mbar_wait(empty_bar + stage, (use - 1) & 1);
