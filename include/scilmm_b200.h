@@ -89,6 +89,12 @@ int slmm_quadform_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
 int slmm_quadform_gram_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols,
                              const double* d_XB, int32_t nb, int32_t row_begin, int32_t row_end, double* d_dots,
                              double* d_gram_half);
+/* CSR sanity check on the device: *flags_out = 0 when every row is strictly increasing and in range
+ * (bit 1: unsorted or duplicate column, bit 2: index / pointer out of range).  scipy hands the reference canonical
+ * CSR (Numerator.py:38 .tocsr()); the engine verifies instead of trusting, without a host scan. */
+int slmm_matset_validate(slmm_matset_t* ms, int32_t k, int32_t* flags_out);
+/* *out = 1 when two device int32 arrays are equal (used to share one pattern between matrices). */
+int slmm_device_arrays_equal_i32(const int32_t* d_a, const int32_t* d_b, int64_t count, int32_t* out);
 /* *out = 1 when A_k equals its transpose bit for bit (device check, cached). */
 int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out);
 int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);

@@ -472,7 +472,7 @@ def he_moments(mat_list, y, MQS=False, matset=None):
         out = ms.he_moments_device(y_dev).cpu().numpy()
     else:       # row blocks balanced by nonzeros + one all-reduce of 2K + 2K^2 doubles
         big = max(range(K), key=lambda k: ms.nnz[k])
-        bounds = _shard.row_blocks_by_nnz(_eng.canonical_csr(mat_list[big]).indptr, world)
+        bounds = _shard.row_blocks_by_nnz(_eng._csr_arrays(mat_list[big])[0], world)
         part = ms.he_moments_device(y_dev, int(bounds[rank]), int(bounds[rank + 1])).clone()
         out = _shard.allreduce_sum_(part).cpu().numpy()
     q_off, q_diag, S_off, S_diag = _eng.MatSet.split_moments(out, K)

@@ -46,6 +46,8 @@ SIGNATURES = {
     "slmm_matset_pattern_id": (C.c_int, [vp, i32, C.POINTER(i32)]),
     "slmm_quadform_multi": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, vp]),
     "slmm_matset_is_symmetric": (C.c_int, [vp, i32, C.POINTER(i32)]),
+    "slmm_matset_validate": (C.c_int, [vp, i32, C.POINTER(i32)]),
+    "slmm_device_arrays_equal_i32": (C.c_int, [vp, vp, i64, C.POINTER(i32)]),
     "slmm_quadform_gram_multi": (C.c_int, [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp]),
     "slmm_chol_analyze": (C.c_int, [i32, vp, vp, i32, vp, pp]),
     "slmm_chol_destroy": (C.c_int, [vp]),

@@ -607,6 +607,35 @@ __global__ void __launch_bounds__(256) symmetry_check_kernel(const int32_t* __re
   }
 }
 
+// CSR sanity on the device (the host never scans the 10^8-entry index arrays): rows strictly increasing (sorted, no
+// duplicates), indices inside [0,n), row pointers monotone.  flag bits: 1 unsorted/duplicate, 2 out of range.
+__global__ void __launch_bounds__(256) csr_validate_kernel(const int32_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ indices, int n, int64_t nnz,
+                                                           int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  int bad = 0;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    if (b > e || b < 0 || (int64_t)e > nnz) { bad |= 2; continue; }
+    for (int p = b + lane; p < e; p += 32) {
+      const int c = indices[p];
+      if (c < 0 || c >= n) bad |= 2;
+      if (p + 1 < e && indices[p + 1] <= c) bad |= 1;
+    }
+  }
+  if (bad) atomicOr(flag, bad);
+}
+
+// exact comparison of two index arrays (pattern sharing between e.g. IBD and its Hadamard square)
+__global__ void __launch_bounds__(256) arrays_differ_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                                                            int64_t count, int* __restrict__ flag) {
+  int bad = 0;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < count; q += (int64_t)gridDim.x * blockDim.x)
+    if (a[q] != b[q]) bad = 1;
+  if (bad) *flag = 1;
+}
+
 }  // namespace slmm
 
 using namespace slmm;
@@ -958,6 +987,40 @@ int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, con
   else if (cpl <= 4) { GROUP_CASE(4) } else { GROUP_CASE(5) }
 #undef GROUP_CASE
   CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_validate(slmm_matset_t* ms, int32_t k, int32_t* flags_out) {
+  SLMM_TRY
+  if (!ms || k < 0 || k >= ms->K || !flags_out || !ms->m[k].data) throw std::invalid_argument("bad arguments");
+  const CsrDev& c = ms->m[k];
+  int* d_flag = dev_alloc<int>(1);
+  CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
+  csr_validate_kernel<<<he_grid(ms->n), 256>>>(c.indptr, c.indices, ms->n, c.nnz, d_flag);
+  g_launch_count++;
+  int flag = 0;
+  CUDA_OK(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  dev_free(d_flag);
+  *flags_out = flag;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_device_arrays_equal_i32(const int32_t* d_a, const int32_t* d_b, int64_t count, int32_t* out) {
+  SLMM_TRY
+  if (!d_a || !d_b || !out || count < 0) throw std::invalid_argument("bad arguments");
+  int* d_flag = dev_alloc<int>(1);
+  CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
+  if (count > 0) {
+    const int grid = (int)std::min<int64_t>((count + 255) / 256, 148 * 16);
+    arrays_differ_kernel<<<grid, 256>>>(d_a, d_b, count, d_flag);
+    g_launch_count++;
+  }
+  int flag = 1;
+  CUDA_OK(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  dev_free(d_flag);
+  *out = flag ? 0 : 1;
   return SLMM_OK;
   SLMM_CATCH
 }

@@ -112,12 +112,30 @@ class SymbolicView(object):
 
 
 # ------------------------------------------------------------------------------------------------ matrices
+def _csr_arrays(m):
+    """(indptr, indices, data, nnz) of a scipy CSR matrix as int32/int32/float64 contiguous arrays WITHOUT scanning
+    them on the host (sortedness and ranges are verified on the device after the upload)."""
+    if not sp.isspmatrix_csr(m):
+        m = sp.csr_matrix(m)
+    ip, ix, dt = m.indptr, m.indices, m.data
+    if ip.dtype != np.int32:
+        ip = ip.astype(np.int32)
+    if ix.dtype != np.int32:
+        ix = ix.astype(np.int32)
+    if dt.dtype != np.float64:
+        dt = dt.astype(np.float64)
+    return np.ascontiguousarray(ip), np.ascontiguousarray(ix), np.ascontiguousarray(dt), int(m.nnz)
+
+
 class MatSet(object):
-    """K CSR relationship matrices resident in HBM (slmm_matset_t)."""
+    """K CSR relationship matrices resident in HBM (slmm_matset_t).
+
+    The host never scans the index arrays: uploads go through pinned staging, pattern sharing (IBD and its
+    Hadamard square) is decided by an exact comparison ON THE DEVICE, and so is the CSR sanity check (sorted rows,
+    indices in range); a matrix that fails it is canonicalised by scipy and uploaded again."""
 
     def __init__(self, mats):
         torch = require_cuda()
-        mats = [canonical_csr(m) for m in mats]
         self.n = mats[0].shape[0]
         self.K = len(mats)
         h = C.c_void_p()
@@ -126,29 +144,54 @@ class MatSet(object):
         self._keep = []
         self.nnz = []
         self.h2d_bytes = 0
-        patterns = []
+        patterns = []                     # (k, indptr_host, nnz, ptr_t, idx_t)
         for k, m in enumerate(mats):
             if m.shape != (self.n, self.n):
                 raise ValueError("all matrices must be n x n")
-            same = -1
-            for j, (pj, ptr_t, idx_t) in enumerate(patterns):
-                if pj.nnz == m.nnz and (pj.indptr is m.indptr or np.array_equal(pj.indptr, m.indptr)) and \
-                        (pj.indices is m.indices or np.array_equal(pj.indices, m.indices)):
-                    same = j
-                    break
-            if same >= 0:
-                ptr_t, idx_t = patterns[same][1], patterns[same][2]
-            else:
-                ptr_t, idx_t = to_device(m.indptr, torch), to_device(m.indices, torch)
-                self.h2d_bytes += m.indptr.nbytes + m.indices.nbytes
-            dat_t = to_device(m.data, torch)
-            self.h2d_bytes += m.data.nbytes
-            patterns.append((m, ptr_t, idx_t))
-            self._keep.append((ptr_t, idx_t, dat_t))
-            self.nnz.append(int(m.nnz))
-            check(lib().slmm_matset_bind_device(h, k, ptr_t.data_ptr(), idx_t.data_ptr(), dat_t.data_ptr(),
-                                                int(m.nnz), same))
+            self._bind(k, m, patterns, torch, verified=False)
         self._out = torch.zeros(2 * self.K + 2 * self.K * self.K, dtype=torch.float64, device="cuda")
+
+    def _bind(self, k, m, patterns, torch, verified):
+        ip, ix, dt, nnz = _csr_arrays(m)
+        dat_t = to_device(dt, torch)
+        self.h2d_bytes += dt.nbytes
+        same = -1
+        ptr_t = idx_t = None
+        for (j, ipj, nnzj, ptr_j, idx_j) in patterns:
+            if nnzj != nnz or not (ipj is ip or np.array_equal(ipj, ip)):       # row pointers: 4(n+1) bytes, cheap
+                continue
+            if idx_t is None:
+                idx_t = to_device(ix, torch)
+                self.h2d_bytes += ix.nbytes
+            eq = C.c_int32(0)
+            check(lib().slmm_device_arrays_equal_i32(idx_j.data_ptr(), idx_t.data_ptr(), nnz, C.byref(eq)))
+            if eq.value:
+                same, ptr_t, idx_t = j, ptr_j, idx_j
+                break
+        if same < 0:
+            ptr_t = to_device(ip, torch)
+            if idx_t is None:
+                idx_t = to_device(ix, torch)
+                self.h2d_bytes += ix.nbytes
+            self.h2d_bytes += ip.nbytes
+        check(lib().slmm_matset_bind_device(self._h, k, ptr_t.data_ptr(), idx_t.data_ptr(), dat_t.data_ptr(), nnz, same))
+        if same < 0 and not verified:
+            flags = C.c_int32(0)
+            check(lib().slmm_matset_validate(self._h, k, C.byref(flags)))
+            if flags.value & 2:
+                raise ValueError("matrix %d: CSR indices / row pointers out of range" % k)
+            if flags.value & 1:       # unsorted rows or duplicates: let scipy canonicalise, upload again
+                mc = sp.csr_matrix(m).copy()
+                mc.sum_duplicates()
+                return self._bind(k, canonical_csr(mc), patterns, torch, verified=True)
+        if same < 0:
+            patterns.append((k, ip, nnz, ptr_t, idx_t))
+        if len(self._keep) > k:
+            self._keep[k] = (ptr_t, idx_t, dat_t)
+            self.nnz[k] = nnz
+        else:
+            self._keep.append((ptr_t, idx_t, dat_t))
+            self.nnz.append(nnz)
 
     def values_ptr(self, k):
         return self._keep[k][2].data_ptr()

@@ -127,6 +127,34 @@ def test_spmm_and_coldot(golden_c1mini, eng):
 
 
 
+def test_matset_device_validation_and_pattern_sharing(golden_c1mini, eng):
+    """Unsorted / duplicated CSR input is detected on the device and canonicalised; equal patterns are shared."""
+    import scipy.sparse as sp
+    g = golden_c1mini
+    A, E_ = g.csr("A"), g.csr("E")
+    rng = np.random.default_rng(2)
+    # same matrix with every row's entries shuffled (has_sorted_indices is False, values are identical)
+    ip = A.indptr
+    perm = np.concatenate([ip[r] + rng.permutation(ip[r + 1] - ip[r]) for r in range(g.n)])
+    Au = sp.csr_matrix((A.data[perm], A.indices[perm], ip.copy()), shape=A.shape)
+    # duplicates: every entry split in two adjacent entries (rows non-decreasing, not strictly increasing)
+    dd = np.empty(2 * A.nnz)
+    dd[0::2], dd[1::2] = 0.25 * A.data, 0.75 * A.data
+    Adup = sp.csr_matrix((dd, np.repeat(A.indices, 2), (2 * A.indptr).astype(np.int32)), shape=A.shape)
+    y = eng.to_device(g["y"])
+    ref = eng.MatSet([A, E_]).he_moments_device(y).cpu().numpy().copy()
+    ms = eng.MatSet([Au, E_])
+    assert ms.pattern_id(0) == ms.pattern_id(1)            # shared after canonicalisation
+    assert rel_err(ms.he_moments_device(y).cpu().numpy(), ref) < 1e-12
+    ms2 = eng.MatSet([Adup, E_])
+    assert ms2.pattern_id(0) == ms2.pattern_id(1)
+    assert rel_err(ms2.he_moments_device(y).cpu().numpy(), ref) < 1e-12
+    bad = sp.csr_matrix((np.ones(1), np.array([g.n + 5], dtype=np.int32),
+                         np.concatenate([[0], np.ones(g.n, dtype=np.int32)]).astype(np.int32)), shape=A.shape)
+    with pytest.raises(ValueError):
+        eng.MatSet([bad])
+
+
 def test_quadform_symmetric_half_and_general_pass(golden_c1mini, eng):
     """x' A x per column: symmetric matrices are traversed on/below the diagonal only, a non-symmetric matrix takes
     the general pass; row shards add up (reference :65-66)."""
