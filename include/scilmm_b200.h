@@ -138,6 +138,9 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, dou
  * Profiling mode brackets every launch of the factor / solve schedules with CUDA events on the launching stream and
  * sums the time per kernel kind: 0 potrf+inverse, 1 DMMA GEMM 128x128 tiles, 2 DMMA GEMM 64x64 tiles,
  * 3 extend-add (warp per item), 4 RHS pull, 5 extend-add (CTA per item, large parents).  flops6 = dense flops issued per kind. */
+/* raw supernodal panels (lsize doubles, layout of slmm_symbolic_arrays' sn_lptr / sn_nrow): parity tests compare
+ * them supernode by supernode with the CPU oracle */
+int slmm_chol_copy_panels(slmm_chol_t* h, double* host_out);
 int slmm_launch_count(int64_t* out, int32_t reset);
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on);
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6);

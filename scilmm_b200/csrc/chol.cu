@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(TPI < 128 ? 128 : TPI) extend_add_kernel(const
       }
       for (; u < rsc; u += TPI) dst[relc[u]] += src[u];
     }
+    // Two children can hit the same parent entry, and the thread that owns an entry differs from child to child:
+    // the group must finish one child's read-modify-writes before any of its threads starts the next child.
+    if (TPI >= 128) __syncthreads(); else __syncwarp();
   }
 }
 
@@ -1085,6 +1088,14 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* colptr, int32_t* rowidx, double*
     }
   }
   colptr[S.n] = q;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_copy_panels(slmm_chol_t* h, double* host_out) {
+  SLMM_TRY
+  if (!h || !host_out) throw std::invalid_argument("null argument");
+  CUDA_OK(cudaMemcpy(host_out, h->Lx, h->S.lsize * sizeof(double), cudaMemcpyDeviceToHost));
   return SLMM_OK;
   SLMM_CATCH
 }

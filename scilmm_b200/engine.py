@@ -398,6 +398,12 @@ class CholEngine(object):
         check(lib().slmm_chol_lmul(self._h, Z2.data_ptr(), out.data_ptr(), int(Z2.shape[1])))
         return out if Z.dim() == 2 else out[:, 0]
 
+    def panels(self):
+        """Raw supernodal panels as one host array (layout: SymbolicView.arrays() sn_lptr / sn_nrow)."""
+        out = np.zeros(self.stats()["lsize"], dtype=np.float64)
+        check(lib().slmm_chol_copy_panels(self._h, np_ptr(out)))
+        return out
+
     def set_profiling(self, on):
         check(lib().slmm_chol_set_profiling(self._h, 1 if on else 0))
 

@@ -266,6 +266,37 @@ def test_wide_supernodes_and_many_rhs(slmm, eng):
         assert rel_err(X, np.linalg.solve(V.toarray(), Bm)) < 1e-10
 
 
+@pytest.mark.parametrize("border", [300, 700])
+def test_extend_add_many_children_same_targets(slmm, eng, border):
+    """Block-arrow matrix: 40 leaf supernodes whose update matrices all land on the SAME entries of one parent
+    front (border >= 512 rows takes the CTA-per-item extend-add, < 512 the warp-per-item one).  Lost updates between
+    children show up as a wrong factor; repeated factorizations must agree bit for bit."""
+    rng = np.random.default_rng(9)
+    nleaf, bs = 40, 20
+    n = nleaf * bs + border
+    V = np.zeros((n, n))
+    for b in range(nleaf):
+        G = rng.standard_normal((bs, bs))
+        V[b * bs:(b + 1) * bs, b * bs:(b + 1) * bs] = G @ G.T / bs + 2 * np.eye(bs)
+        C = 0.05 * rng.standard_normal((border, bs))
+        V[nleaf * bs:, b * bs:(b + 1) * bs] = C
+        V[b * bs:(b + 1) * bs, nleaf * bs:] = C.T
+    G = rng.standard_normal((border, border))
+    V[nleaf * bs:, nleaf * bs:] = G @ G.T / border + 3 * np.eye(border)
+    Vs = sp.csc_matrix(V)
+    chol = slmm.SparseCholesky(ordering_method="natural")
+    Ls = []
+    for rep in range(3):
+        f = chol(Vs)
+        Ls.append(f.L().toarray())
+    assert np.array_equal(Ls[0], Ls[1]) and np.array_equal(Ls[0], Ls[2])
+    assert rel_err(Ls[0] @ Ls[0].T, V) < 1e-12
+    sign, ld = np.linalg.slogdet(V)
+    assert abs(f.logdet() - ld) < 1e-10 * abs(ld)
+    b = rng.standard_normal((n, 3))
+    assert rel_err(f(b), np.linalg.solve(V, b)) < 1e-10
+
+
 def test_lookahead_streams_dense_front(slmm, eng):
     """A 2300-column dense front with rows below it: outer blocks 0..4, so the trailing updates are split between the
     main and the bulk stream (look-ahead).  Factor twice and compare bit for bit (no races, fixed summation
