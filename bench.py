@@ -350,6 +350,23 @@ def main():
         "profile_ms": {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]},
     }
 
+    # ---------------- size-independent parity properties at the full BASELINE size: the factor is
+    # bit-reproducible (no atomics, fixed summation order), V x = b holds for the solves, L*Z followed by the solve
+    # round-trips, and (below, when the CPU arm runs) nll agrees with the oracle on the same inputs
+    def factor_logdet():
+        assemble()
+        ses.eng.factorize()
+        return ses.eng.logdet()
+    ld1, ld2 = factor_logdet(), factor_logdet()
+    Bchk = torch.randn(n, 8, dtype=torch.float64, device="cuda")
+    Xchk = ses.eng.solve_(Bchk.clone())
+    VX = sum(float(sig[k]) * ses.matset.spmm(k, Xchk) for k in range(K))
+    solve_res = float((VX - Bchk).abs().max() / Bchk.abs().max())
+    parity = {"logdet": ld1, "logdet_bitwise_repeatable": bool(ld1 == ld2), "solve_residual_rel": solve_res,
+              "solve_residual_ok": bool(solve_res < 1e-10)}
+    if not (parity["logdet_bitwise_repeatable"] and parity["solve_residual_ok"]):
+        raise RuntimeError("parity check failed at full size: %r" % (parity,))
+
     # ---------------- e2e through the public API with host buffers
     chol_h = S.SparseCholesky(rng="host_buffer")
     chol_h._engines = chol._engines                      # same analysis; the session re-registers patterns
@@ -381,11 +398,15 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         r = cpu_reml_sample(mats, cov, ys, sig, True, s, args.cpu_cols)
         log("cpu parts", r["parts"])
+        if abs(r["nll"] - nll_h) > 1e-10 * abs(r["nll"]) or abs(r["logdet"] - parity["logdet"]) > 1e-10 * abs(r["logdet"]):
+            raise RuntimeError("GPU result differs from the CPU oracle beyond 1e-10: nll %r vs %r, logdet %r vs %r"
+                               % (nll_h, r["nll"], parity["logdet"], r["logdet"]))
         cpu = {"value": round(r["seconds_with_reanalysis"], 2), "unit": "s", "cores": os.cpu_count(), "kind": "port",
                "value_analysis_cached": round(r["seconds"], 2),
                "parts_s": {k: round(v, 2) for k, v in r["parts"].items()},
                "cholesky_gflops": round(r["flops"] / r["parts"]["factor"] / 1e9, 1),
                "nll_rel_diff_vs_gpu": abs(r["nll"] - nll_h) / abs(r["nll"]),
+               "logdet_rel_diff_vs_gpu": abs(r["logdet"] - parity["logdet"]) / abs(r["logdet"]),
                "sample": "oracle port (CHOLMOD is not installed): full assembly, METIS analysis, supernodal LAPACK "
                          "factorization on all cores, logdet, deterministic solves; probe pipeline on %d of %d "
                          "columns scaled x%g; value includes the per-evaluation re-analysis the reference performs"
@@ -402,7 +423,7 @@ def main():
                           "symbolic_s": round(st["t_order"] + st["t_symbolic"], 2), "session_setup_s": round(setup_s, 1),
                           "parallelism": "probe columns sharded x%d, factor replicated" % world},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-               "phases": phases, "cpu_baseline": cpu, "he": he,
+               "phases": phases, "parity": parity, "cpu_baseline": cpu, "he": he,
                "nll": float(nll), "grad": [float(g) for g in grad]}
         print(json.dumps(out))
     if world > 1:

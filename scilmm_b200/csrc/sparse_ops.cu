@@ -23,6 +23,7 @@ struct CsrDev {
   std::vector<int32_t> h_indptr;   // kept for pattern comparison (uploaded matrices only)
   uint64_t idx_hash = 0;
   int symmetric = -1;      // -1 unknown, 0 no, 1 yes (checked on the device on first use)
+  int32_t* rend = nullptr; // per row: one past the last entry with col <= row (pattern leaders only, built lazily)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -46,7 +47,10 @@ struct GroupArgs {
 
 template <int G>
 __global__ void __launch_bounds__(256) he_group_kernel(GroupArgs<G> a, const double* __restrict__ y, int row_begin,
-                                                       int row_end, double* __restrict__ partial) {
+                                                       int row_end, double* __restrict__ partial,
+                                                       const int32_t* __restrict__ rend, double off_scale) {
+  // rend != nullptr: symmetric matrices, only the entries with col <= row are read (rend[row] = one past the last
+  // of them) and the off-diagonal sums are doubled at the end (off_scale = 2): half the index / value traffic.
   constexpr int UN = 4;
   constexpr int NP = G * (G + 1) / 2;
   constexpr int NV = 2 * G + 2 * NP;
@@ -60,12 +64,12 @@ __global__ void __launch_bounds__(256) he_group_kernel(GroupArgs<G> a, const dou
   int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   int nb = 0, ne = 0;
   double nyi = 0.0;
-  if (row < row_end) { nb = a.indptr[row]; ne = a.indptr[row + 1]; nyi = y[row]; }
+  if (row < row_end) { nb = a.indptr[row]; ne = rend ? rend[row] : a.indptr[row + 1]; nyi = y[row]; }
   for (; row < row_end; row += warps) {
     const int b = nb, e = ne;
     const double yi = nyi;
     if (row + warps < row_end) {         // row pointers of the next row are fetched under this row's loads
-      nb = a.indptr[row + warps]; ne = a.indptr[row + warps + 1]; nyi = y[row + warps];
+      nb = a.indptr[row + warps]; ne = rend ? rend[row + warps] : a.indptr[row + warps + 1]; nyi = y[row + warps];
     }
     double rowacc[G];
 #pragma unroll
@@ -113,9 +117,9 @@ __global__ void __launch_bounds__(256) he_group_kernel(GroupArgs<G> a, const dou
   const int warp = threadIdx.x >> 5;
   double vals[NV];
 #pragma unroll
-  for (int g = 0; g < G; g++) { vals[g] = qo[g]; vals[G + g] = qd[g]; }
+  for (int g = 0; g < G; g++) { vals[g] = qo[g] * off_scale; vals[G + g] = qd[g]; }
 #pragma unroll
-  for (int p = 0; p < NP; p++) { vals[2 * G + p] = so[p]; vals[2 * G + NP + p] = sd[p]; }
+  for (int p = 0; p < NP; p++) { vals[2 * G + p] = so[p] * off_scale; vals[2 * G + NP + p] = sd[p]; }
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     const double s = warp_sum(vals[k]);
@@ -174,10 +178,11 @@ __global__ void __launch_bounds__(256) he_cross_kernel(const int32_t* __restrict
 __global__ void __launch_bounds__(256) he_short_kernel(const int32_t* __restrict__ indptr,
                                                        const int32_t* __restrict__ indices,
                                                        const double* __restrict__ data, const double* __restrict__ y,
-                                                       int row_begin, int row_end, double* __restrict__ partial) {
+                                                       int row_begin, int row_end, double* __restrict__ partial,
+                                                       const int32_t* __restrict__ rend, double off_scale) {
   double qo = 0.0, qd = 0.0, so = 0.0, sd = 0.0;
   for (int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += gridDim.x * blockDim.x) {
-    const int b = indptr[row], e = indptr[row + 1];
+    const int b = indptr[row], e = rend ? rend[row] : indptr[row + 1];
     const double yi = y[row];
     double acc = 0.0;
     for (int p = b; p < e; p++) {
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) he_short_kernel(const int32_t* __restrict
   }
   __shared__ double sh[8][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  qo = warp_sum(qo); qd = warp_sum(qd); so = warp_sum(so); sd = warp_sum(sd);
+  qo = warp_sum(qo) * off_scale; qd = warp_sum(qd); so = warp_sum(so) * off_scale; sd = warp_sum(sd);
   if (lane == 0) { sh[warp][0] = qo; sh[warp][1] = qd; sh[warp][2] = so; sh[warp][3] = sd; }
   __syncthreads();
   if (threadIdx.x < 4) {
@@ -235,7 +240,8 @@ __global__ void __launch_bounds__(256) he_cross_short_kernel(const int32_t* __re
 // TPR = true: thread per probe row (short rows), false: warp per probe row.  partial: [GP*GT][off, diag] per CTA.
 template <int GP, int GT, bool TPR>
 __global__ void __launch_bounds__(256) he_cross_multi_kernel(GroupArgs<GP> pr, GroupArgs<GT> tg, int row_begin,
-                                                             int row_end, double* __restrict__ partial) {
+                                                             int row_end, double* __restrict__ partial,
+                                                             const int32_t* __restrict__ rend, double off_scale) {
   constexpr int NV = GP * GT * 2;
   double acc[NV];
 #pragma unroll
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(256) he_cross_multi_kernel(GroupArgs<GP> pr, G
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   const int first = TPR ? gtid : (gtid >> 5), step = TPR ? gthreads : (gthreads >> 5);
   for (int row = row_begin + first; row < row_end; row += step) {
-    const int sb = pr.indptr[row], se = pr.indptr[row + 1], lb = tg.indptr[row], le = tg.indptr[row + 1];
+    const int sb = pr.indptr[row], se = rend ? rend[row] : pr.indptr[row + 1], lb = tg.indptr[row], le = tg.indptr[row + 1];
     for (int p = sb + (TPR ? 0 : lane); p < se; p += (TPR ? 1 : 32)) {
       const int col = pr.indices[p];
       int lo = lb, hi = le;
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(256) he_cross_multi_kernel(GroupArgs<GP> pr, G
   __shared__ double sh[8][NV];
 #pragma unroll
   for (int k = 0; k < NV; k++) {
-    const double v = warp_sum(acc[k]);
+    const double v = warp_sum(acc[k]) * ((k & 1) ? 1.0 : off_scale);     // even slots: off-diagonal sums
     if (lane == 0) sh[warp][k] = v;
   }
   __syncthreads();
@@ -607,6 +613,17 @@ __global__ void __launch_bounds__(256) symmetry_check_kernel(const int32_t* __re
   }
 }
 
+// rend[row] = one past the last entry of the (sorted) row with col <= row
+__global__ void __launch_bounds__(256) row_end_kernel(const int32_t* __restrict__ indptr,
+                                                      const int32_t* __restrict__ indices, int n,
+                                                      int32_t* __restrict__ rend) {
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    int lo = indptr[row], hi = indptr[row + 1];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (indices[mid] <= row) lo = mid + 1; else hi = mid; }
+    rend[row] = lo;
+  }
+}
+
 // CSR sanity on the device (the host never scans the 10^8-entry index arrays): rows strictly increasing (sorted, no
 // duplicates), indices inside [0,n), row pointers monotone.  flag bits: 1 unsorted/duplicate, 2 out of range.
 __global__ void __launch_bounds__(256) csr_validate_kernel(const int32_t* __restrict__ indptr,
@@ -676,7 +693,8 @@ static int he_grid(int rows) {
 }
 
 template <int G>
-static void launch_group(slmm_matset* ms, const int* members, const double* d_y, int r0, int r1, double* d_out) {
+static void launch_group(slmm_matset* ms, const int* members, const double* d_y, int r0, int r1, double* d_out,
+                         const int32_t* rend) {
   const int K = ms->K;
   constexpr int NP = G * (G + 1) / 2, NV = 2 * G + 2 * NP;
   GroupArgs<G> a;
@@ -685,7 +703,7 @@ static void launch_group(slmm_matset* ms, const int* members, const double* d_y,
   for (int g = 0; g < G; g++) a.data[g] = ms->m[members[g]].data;
   const int grid = he_grid(r1 - r0);
   double* part = ms->partial((size_t)grid * NV);
-  he_group_kernel<G><<<grid, 256>>>(a, d_y, r0, r1, part);
+  he_group_kernel<G><<<grid, 256>>>(a, d_y, r0, r1, part, rend, rend ? 2.0 : 1.0);
   // destination indices inside [q_off | q_diag | S_off | S_diag]
   std::vector<int32_t> dst(NV);
   for (int g = 0; g < G; g++) { dst[g] = members[g]; dst[G + g] = K + members[g]; }
@@ -745,6 +763,7 @@ int slmm_matset_destroy(slmm_matset_t* ms) {
   for (auto& c : ms->m) {
     if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
     if (c.owned_data) dev_free((void*)c.data);
+    dev_free(c.rend);
   }
   dev_free(ms->d_partial); dev_free(ms->d_y); dev_free(ms->d_out); dev_free(ms->d_dst);
   delete ms;
@@ -757,6 +776,7 @@ int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* indptr, cons
   CsrDev& c = ms->m[k];
   if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
   if (c.owned_data) dev_free((void*)c.data);
+  dev_free(c.rend);
   c = CsrDev();
   const int n = ms->n;
   c.nnz = indptr[n];
@@ -791,6 +811,7 @@ int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indpt
   CsrDev& c = ms->m[k];
   if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
   if (c.owned_data) dev_free((void*)c.data);
+  dev_free(c.rend);
   c = CsrDev();
   c.indptr = d_indptr; c.indices = d_indices; c.data = d_data; c.nnz = nnz;
   c.pattern = same_as >= 0 ? ms->m[same_as].pattern : k;
@@ -818,6 +839,26 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
   for (int k = 0; k < K; k++)
     if (!ms->m[k].data) throw std::invalid_argument("matrix not set");
   CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * (2 * K + 2 * K * K), 0));
+  // Symmetric matrices (checked once per matrix on the device): every pass reads only the entries on and below
+  // the diagonal and doubles the off-diagonal sums.
+  bool sym_all = true;
+  for (int k = 0; k < K && sym_all; k++) {
+    int32_t f = 0;
+    const int rc = slmm_matset_is_symmetric(ms, k, &f);
+    if (rc != SLMM_OK) return rc;
+    sym_all = f != 0;
+  }
+  auto row_ends = [&](int k) -> const int32_t* {
+    if (!sym_all) return nullptr;
+    CsrDev& lead = ms->m[ms->m[k].pattern];
+    if (!lead.rend) {
+      lead.rend = dev_alloc<int32_t>(ms->n);
+      row_end_kernel<<<std::min(148 * 8, (ms->n + 255) / 256), 256>>>(lead.indptr, lead.indices, ms->n, lead.rend);
+      g_launch_count++;
+    }
+    return lead.rend;
+  };
+  const double off_scale = sym_all ? 2.0 : 1.0;
   // pattern groups
   std::vector<char> done(K, 0);
   for (int k = 0; k < K; k++) {
@@ -832,7 +873,7 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         const int rows = r1 - r0;
         const int grid = std::max(1, std::min(148 * 8, (rows + 255) / 256));
         double* part = ms->partial((size_t)grid * 4);
-        he_short_kernel<<<grid, 256>>>(lead.indptr, lead.indices, lead.data, d_y, r0, r1, part);
+        he_short_kernel<<<grid, 256>>>(lead.indptr, lead.indices, lead.data, d_y, r0, r1, part, row_ends(members[g0]), off_scale);
         const int k0 = members[g0];
         const int32_t dst[4] = {k0, K + k0, 2 * K + k0 * K + k0, 2 * K + K * K + k0 * K + k0};
         CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
@@ -841,10 +882,10 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         continue;
       }
       switch (gn) {
-        case 1: launch_group<1>(ms, members + g0, d_y, r0, r1, d_out); break;
-        case 2: launch_group<2>(ms, members + g0, d_y, r0, r1, d_out); break;
-        case 3: launch_group<3>(ms, members + g0, d_y, r0, r1, d_out); break;
-        default: launch_group<4>(ms, members + g0, d_y, r0, r1, d_out); break;
+        case 1: launch_group<1>(ms, members + g0, d_y, r0, r1, d_out, row_ends(members[g0])); break;
+        case 2: launch_group<2>(ms, members + g0, d_y, r0, r1, d_out, row_ends(members[g0])); break;
+        case 3: launch_group<3>(ms, members + g0, d_y, r0, r1, d_out, row_ends(members[g0])); break;
+        default: launch_group<4>(ms, members + g0, d_y, r0, r1, d_out, row_ends(members[g0])); break;
       }
     }
   }
@@ -881,6 +922,7 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         const std::vector<int>& P = ms->m[chunks[a][0]].nnz <= ms->m[chunks[b][0]].nnz ? chunks[a] : chunks[b];
         const std::vector<int>& T = (&P == &chunks[a]) ? chunks[b] : chunks[a];
         const bool tpr = ms->m[P[0]].nnz < (int64_t)8 * ms->n;
+        const int32_t* prend = row_ends(P[0]);
         const int gp = (int)P.size(), gt = (int)T.size(), nv = gp * gt * 2;
         const int rows = r1 - r0;
         const int grid = tpr ? std::max(1, std::min(148 * 8, (rows + 255) / 256)) : he_grid(rows);
@@ -896,8 +938,8 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         p1.indptr = pa.indptr; p1.indices = pa.indices; p1.data[0] = pa.data[0];
         t1.indptr = ta.indptr; t1.indices = ta.indices; t1.data[0] = ta.data[0];
 #define CROSS(GP_, GT_, PA_, TA_)                                                                              \
-        if (tpr) he_cross_multi_kernel<GP_, GT_, true><<<grid, 256>>>(PA_, TA_, r0, r1, part);                     \
-        else he_cross_multi_kernel<GP_, GT_, false><<<grid, 256>>>(PA_, TA_, r0, r1, part);
+        if (tpr) he_cross_multi_kernel<GP_, GT_, true><<<grid, 256>>>(PA_, TA_, r0, r1, part, prend, off_scale);   \
+        else he_cross_multi_kernel<GP_, GT_, false><<<grid, 256>>>(PA_, TA_, r0, r1, part, prend, off_scale);
         if (gp == 1 && gt == 1) { CROSS(1, 1, p1, t1) }
         else if (gp == 1 && gt == 2) { CROSS(1, 2, p1, ta) }
         else if (gp == 2 && gt == 1) { CROSS(2, 1, pa, t1) }
