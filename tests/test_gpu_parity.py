@@ -297,22 +297,32 @@ def test_extend_add_many_children_same_targets(slmm, eng, border):
     assert rel_err(f(b), np.linalg.solve(V, b)) < 1e-10
 
 
-def test_lookahead_streams_dense_front(slmm, eng):
-    """A 2300-column dense front with rows below it: outer blocks 0..4, so the trailing updates are split between the
-    main and the bulk stream (look-ahead).  Factor twice and compare bit for bit (no races, fixed summation
+@pytest.mark.parametrize("dense_first", [False, True])
+def test_lookahead_streams_dense_front(slmm, eng, dense_first):
+    """A 2300-column dense front: outer blocks 0..4, so the trailing updates are split between the main and the bulk
+    stream (look-ahead).  dense_first=True puts 300 coupled rows BELOW the wide supernode, so its Schur complement is
+    built block by block on the third stream.  Factor twice and compare bit for bit (no races, fixed summation
     order), then check logdet / solve against LAPACK."""
     rng = np.random.default_rng(5)
-    nd, nt = 2300, 400
+    nd, nt, nc = 2300, 400, 300 if dense_first else 60
     B = rng.standard_normal((nd, nd))
     D = B @ B.T / nd + 2.0 * np.eye(nd)
     T = sp.random(nt, nt, 0.02, random_state=1)
     T = (T + T.T + 20 * sp.eye(nt)).toarray()
+    if dense_first:
+        T[:nc, :nc] += 0.01       # make the coupled rows one clique, as the fill will
     V = np.zeros((nd + nt, nd + nt))
-    V[nt:, nt:] = D
-    V[:nt, :nt] = T
-    C = 0.01 * rng.standard_normal((nd, 60))
-    V[nt:, :60] = C
-    V[:60, nt:] = C.T
+    C = 0.01 * rng.standard_normal((nd, nc))
+    if dense_first:
+        V[:nd, :nd] = D
+        V[nd:, nd:] = T
+        V[:nd, nd:nd + nc] = C
+        V[nd:nd + nc, :nd] = C.T
+    else:
+        V[nt:, nt:] = D
+        V[:nt, :nt] = T
+        V[nt:, :nc] = C
+        V[:nc, nt:] = C.T
     Vs = sp.csc_matrix(V)
     chol = slmm.SparseCholesky(ordering_method="natural")
     f = chol(Vs)
