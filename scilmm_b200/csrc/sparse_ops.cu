@@ -4,6 +4,7 @@
 // reference scilmm/SparseCholesky.py:65,66,70 (compute_gradients), :157,:161 (compute_hess), :223,:229 (HE).
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -268,6 +269,67 @@ __global__ void __launch_bounds__(256) he_cross_multi_kernel(GroupArgs<GP> pr, G
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     const double v = warp_sum(acc[k]) * ((k & 1) ? 1.0 : off_scale);     // even slots: off-diagonal sums
+    if (lane == 0) sh[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s2 = 0.0;
+    for (int w = 0; w < 8; w++) s2 += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * NV + threadIdx.x] = s2;
+  }
+}
+
+// Position map of one pattern inside another (built once per pattern pair and cached: patterns do not change
+// between HE calls): map[p] = 2 * (position of probe entry p in the target's arrays) + (1 if diagonal), or -1
+// when the target has no such entry (or, for symmetric sets, when the entry lies above the diagonal).
+__global__ void __launch_bounds__(256) cross_map_kernel(const int32_t* __restrict__ pp, const int32_t* __restrict__ pi,
+                                                        const int32_t* __restrict__ tp, const int32_t* __restrict__ ti,
+                                                        int n, int lower_only, int64_t* __restrict__ map) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const int sb = pp[row], se = pp[row + 1], lb = tp[row], le = tp[row + 1];
+    for (int p = sb + lane; p < se; p += 32) {
+      const int col = pi[p];
+      int64_t out = -1;
+      if (!(lower_only && col > row)) {
+        int lo = lb, hi = le;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ti[mid] < col) lo = mid + 1; else hi = mid; }
+        if (lo < le && ti[lo] == col) out = 2 * (int64_t)lo + (col == row ? 1 : 0);
+      }
+      map[p] = out;
+    }
+  }
+}
+
+// Hadamard dots of GP probe matrices with GT target matrices through the cached position map: a flat, fully
+// coalesced pass over the probe's entries of rows [row_begin,row_end) plus one gather per matched entry.
+// partial: [GP*GT][off, diag] per CTA.
+template <int GP, int GT>
+__global__ void __launch_bounds__(256) he_cross_mapped_kernel(GroupArgs<GP> pr, GroupArgs<GT> tg,
+                                                              const int64_t* __restrict__ map, int row_begin,
+                                                              int row_end, double off_scale,
+                                                              double* __restrict__ partial) {
+  constexpr int NV = GP * GT * 2;
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) acc[k] = 0.0;
+  const int64_t pb = pr.indptr[row_begin], pe = pr.indptr[row_end];
+  for (int64_t p = pb + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pe; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = map[p];
+    if (m < 0) continue;
+    const int64_t t = m >> 1;
+    const int d = (int)(m & 1);
+#pragma unroll
+    for (int gp = 0; gp < GP; gp++)
+#pragma unroll
+      for (int gt = 0; gt < GT; gt++) acc[(gp * GT + gt) * 2 + d] += pr.data[gp][p] * tg.data[gt][t];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double sh[8][NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const double v = warp_sum(acc[k]) * ((k & 1) ? 1.0 : off_scale);
     if (lane == 0) sh[warp][k] = v;
   }
   __syncthreads();
@@ -660,6 +722,7 @@ using namespace slmm;
 struct slmm_matset {
   int n = 0, K = 0;
   std::vector<CsrDev> m;
+  std::map<std::pair<int, int>, int64_t*> cross_maps;   // (probe pattern, target pattern) -> position map (device)
   double* d_partial = nullptr;
   size_t partial_cap = 0;
   double* d_y = nullptr;
@@ -766,6 +829,7 @@ int slmm_matset_destroy(slmm_matset_t* ms) {
     dev_free(c.rend);
   }
   dev_free(ms->d_partial); dev_free(ms->d_y); dev_free(ms->d_out); dev_free(ms->d_dst);
+  for (auto& kv : ms->cross_maps) dev_free(kv.second);
   delete ms;
   return SLMM_OK;
 }
@@ -777,6 +841,8 @@ int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* indptr, cons
   if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
   if (c.owned_data) dev_free((void*)c.data);
   dev_free(c.rend);
+  for (auto& kv : ms->cross_maps) dev_free(kv.second);
+  ms->cross_maps.clear();
   c = CsrDev();
   const int n = ms->n;
   c.nnz = indptr[n];
@@ -812,6 +878,8 @@ int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indpt
   if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
   if (c.owned_data) dev_free((void*)c.data);
   dev_free(c.rend);
+  for (auto& kv : ms->cross_maps) dev_free(kv.second);
+  ms->cross_maps.clear();
   c = CsrDev();
   c.indptr = d_indptr; c.indices = d_indices; c.data = d_data; c.nnz = nnz;
   c.pattern = same_as >= 0 ? ms->m[same_as].pattern : k;
@@ -921,11 +989,17 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         // probe = the side with fewer nonzeros
         const std::vector<int>& P = ms->m[chunks[a][0]].nnz <= ms->m[chunks[b][0]].nnz ? chunks[a] : chunks[b];
         const std::vector<int>& T = (&P == &chunks[a]) ? chunks[b] : chunks[a];
-        const bool tpr = ms->m[P[0]].nnz < (int64_t)8 * ms->n;
-        const int32_t* prend = row_ends(P[0]);
         const int gp = (int)P.size(), gt = (int)T.size(), nv = gp * gt * 2;
-        const int rows = r1 - r0;
-        const int grid = tpr ? std::max(1, std::min(148 * 8, (rows + 255) / 256)) : he_grid(rows);
+        const int lp = ms->m[P[0]].pattern, lt = ms->m[T[0]].pattern;
+        int64_t*& map = ms->cross_maps[std::make_pair(lp, lt)];
+        if (!map) {             // once per pattern pair: where every probe entry sits in the target
+          map = dev_alloc<int64_t>(ms->m[lp].nnz);
+          cross_map_kernel<<<he_grid(ms->n), 256>>>(ms->m[lp].indptr, ms->m[lp].indices, ms->m[lt].indptr,
+                                                    ms->m[lt].indices, ms->n, sym_all ? 1 : 0, map);
+          g_launch_count++;
+        }
+        const int64_t pn = ms->m[lp].nnz;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (pn + 255) / 256));
         double* part = ms->partial((size_t)grid * nv);
         GroupArgs<2> pa, ta;
         pa.indptr = ms->m[P[0]].indptr; pa.indices = ms->m[P[0]].indices;
@@ -937,14 +1011,10 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         GroupArgs<1> p1, t1;
         p1.indptr = pa.indptr; p1.indices = pa.indices; p1.data[0] = pa.data[0];
         t1.indptr = ta.indptr; t1.indices = ta.indices; t1.data[0] = ta.data[0];
-#define CROSS(GP_, GT_, PA_, TA_)                                                                              \
-        if (tpr) he_cross_multi_kernel<GP_, GT_, true><<<grid, 256>>>(PA_, TA_, r0, r1, part, prend, off_scale);   \
-        else he_cross_multi_kernel<GP_, GT_, false><<<grid, 256>>>(PA_, TA_, r0, r1, part, prend, off_scale);
-        if (gp == 1 && gt == 1) { CROSS(1, 1, p1, t1) }
-        else if (gp == 1 && gt == 2) { CROSS(1, 2, p1, ta) }
-        else if (gp == 2 && gt == 1) { CROSS(2, 1, pa, t1) }
-        else { CROSS(2, 2, pa, ta) }
-#undef CROSS
+        if (gp == 1 && gt == 1) he_cross_mapped_kernel<1, 1><<<grid, 256>>>(p1, t1, map, r0, r1, off_scale, part);
+        else if (gp == 1 && gt == 2) he_cross_mapped_kernel<1, 2><<<grid, 256>>>(p1, ta, map, r0, r1, off_scale, part);
+        else if (gp == 2 && gt == 1) he_cross_mapped_kernel<2, 1><<<grid, 256>>>(pa, t1, map, r0, r1, off_scale, part);
+        else he_cross_mapped_kernel<2, 2><<<grid, 256>>>(pa, ta, map, r0, r1, off_scale, part);
         std::vector<int32_t> dst(nv);
         for (int x = 0; x < gp; x++)
           for (int z = 0; z < gt; z++) {
