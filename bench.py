@@ -33,6 +33,18 @@ import scipy.sparse as sp
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+# its version banner there on the first collective), so fd 1 is pointed at stderr for the whole run and the result
+# line goes to a private duplicate of the original stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
+
 # removal fractions found once by simulate_pedigree's bisection (seed 0); avoids repeating the search
 REMOVE_FRAC = {(250000, 1e-3): 0.065625, (100000, 1e-3): 0.084375, (20000, 1e-3): None,
                (1000000, 1e-4): 0.103125}
@@ -41,6 +53,28 @@ REMOVE_FRAC = {(250000, 1e-3): 0.065625, (100000, 1e-3): 0.084375, (20000, 1e-3)
 def log(*a):
     if int(os.environ.get("RANK", "0")) == 0:
         print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def host_mem():
+    try:
+        import psutil
+        vm = psutil.virtual_memory()
+        return "rss %.1f GB, host avail %.0f of %.0f GB" % (psutil.Process().memory_info().rss / 2 ** 30,
+                                                            vm.available / 2 ** 30, vm.total / 2 ** 30)
+    except Exception:
+        return "n/a"
+
+
+def release_host_caches(torch):
+    """Drop what the previous phase pinned / cached (N ranks share one host: 8 x several GB of pinned staging and
+    matrices would otherwise stay resident while the next workload is generated)."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    try:
+        torch._C._host_emptyCache()
+    except Exception:
+        pass
 
 
 def make_inputs(n, sf, ncov, seed=0, with_household=False):
@@ -175,7 +209,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=250000)
+    ap.add_argument("--individuals", dest="n", type=int, default=250000)   # not "--n": torchrun's parser treats it as an ambiguous abbreviation
     ap.add_argument("--sf", type=float, default=1e-3)
     ap.add_argument("--probes", type=int, default=128)
     ap.add_argument("--ncov", type=int, default=10)
@@ -212,14 +246,14 @@ def main():
         sample = ("oracle port: full assembly + METIS analysis + supernodal LAPACK factorization + logdet + "
                   "deterministic solves; probe pipeline on %d of %d columns scaled x%g; analysis repeated per "
                   "evaluation as the reference does" % (args.cpu_cols, args.probes, args.probes / args.cpu_cols))
-        print(json.dumps({"impl": "reference", "metric": "reml_iter_time", "value": v, "unit": "s",
+        emit({"impl": "reference", "metric": "reml_iter_time", "value": v, "unit": "s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": workload, **info},
                           "cpu_baseline": {"value": v, "unit": "s", "cores": os.cpu_count(), "kind": "port",
                                            "sample": sample},
-                          "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -387,6 +421,9 @@ def main():
 
     # ---------------- HE (config 4) secondary result
     he = None
+    log("before HE:", host_mem())
+    del ses, chol, chol_h, Zhost, Bs, Xq, Bchk, Xchk, VX
+    release_host_caches(torch)
     if not args.skip_he:
         try:
             he = bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks)
@@ -425,7 +462,7 @@ def main():
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                "phases": phases, "parity": parity, "cpu_baseline": cpu, "he": he,
                "nll": float(nll), "grad": [float(g) for g in grad]}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -437,7 +474,7 @@ def bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks):
     A, H, cov, y, info = make_inputs(args.he_n, args.he_sf, 2, seed=0, with_household=True)
     n = A.shape[0]
     mats = [A, P.epistasis(A), H]
-    log("HE inputs", info, "nnz(H)", H.nnz)
+    log("HE inputs", info, "nnz(H)", H.nnz, "|", host_mem())
     ms = E.MatSet(mats)
     yd = E.to_device(y)
     bounds = sharding.row_blocks_by_nnz(A.indptr, world)
