@@ -238,3 +238,57 @@ def he_regression(mat_list, cov, y, MQS=False, verbose=False, sim_num=100, compu
             Vq[j, i] = Vq[i, j]
     var = np.linalg.solve(S, np.linalg.solve(S, Vq).T).T
     return est, np.sqrt(np.diag(var))
+
+
+# ----------------------------------------------------------------------------- legacy entry points
+def legacy_lmm(cholesky_func, mats, C, y, with_intercept=True, reml=True, sim_num=100, verbose=False):
+    """reference: scilmm/Estimation/LMM.py:154-171 (LMM) with compute_sigmas :111-124 (equal starting components,
+    no HE start, y not standardised), compute_fixed_effects_p_value :127-131 and compute_sig_of_sig :134-151
+    (the same average-information matrix as SparseCholesky.py:147-168)."""
+    import scipy.stats as stats
+    mats = list(mats) + [sp.eye(y.size).tocsr()]
+    if with_intercept:
+        C = np.hstack((np.ones((y.size, 1)), C))
+    x0 = np.log(np.ones(len(mats)) / len(mats))
+    res = optimize.minimize(lambda x: reml_evaluation(x, cholesky_func, mats, C, y, reml, sim_num, verbose, True),
+                            x0, jac=True, method='L-BFGS-B', options={'eps': 1e-5, 'ftol': 1e-7})
+    sig = np.exp(res.x)
+    factor = cholesky_func(weighted_sum(mats, sig))
+    _, chol_CtViC, _, beta = fixed_effects(factor, y, C)
+    var_beta = la.cho_solve(chol_CtViC, np.eye(C.shape[1]))
+    pvals = stats.f(1, y.shape[0] - 1).sf(beta ** 2 / np.diag(var_beta))
+    se = legacy_sig_of_sig(mats, C, factor, y, sim_num)
+    return {"covariance coefficients": sig, "covariates coefficients": beta, "covariance std": se,
+            "covariates p-values": pvals}
+
+
+def legacy_sig_of_sig(mats, C, factor, y, sim_num):
+    """reference: scilmm/Estimation/LMM.py:134-151 (compute_sig_of_sig).  Unlike SparseCholesky.py:147-168 only the
+    innermost vector is projected: hess[i,j] = -0.5 y' V^-1 A_i V^-1 A_j P y."""
+    K = len(mats)
+    Viy, ViC = factor(y), factor(C)
+    Py = Viy - ViC.dot(np.linalg.inv(C.T.dot(ViC)).dot(C.T.dot(Viy)))
+    F = [factor(mats[j].dot(Py)) for j in range(K)]
+    H = np.empty((K, K))
+    for i in range(K):
+        for j in range(i, K):
+            H[i, j] = H[j, i] = -0.5 * y.dot(factor(mats[i].dot(F[j])))
+    return np.sqrt(np.diag(la.inv(-H)) * (1 + 1.0 / sim_num))
+
+
+def legacy_compute_he(y, C, mats, fit_intercept=False):
+    """reference: scilmm/Estimation/HE.py:22-40 (compute_HE) with regress_beta_out :8-19 (sklearn's
+    LinearRegression restated as a least-squares solve with an optional trailing intercept column)."""
+    X = np.hstack((C, np.ones((C.shape[0], 1)))) if fit_intercept else C
+    coefs, *_ = np.linalg.lstsq(X, y, rcond=None)
+    r = y - X.dot(coefs)
+    n = mats[0].shape[0]
+    off = [sp.csr_matrix(m - m.multiply(sp.eye(n))) for m in mats]
+    m = len(mats)
+    xtx = np.zeros((m, m))
+    for i in range(m):
+        for j in range(i, m):
+            xtx[i, j] = xtx[j, i] = off[i].multiply(off[j]).sum()
+    xty = np.array([r.dot(off[i].dot(r)) for i in range(m)])
+    coef = np.linalg.inv(xtx).dot(xty)
+    return np.append(coef, 1 - coef.sum()), coefs.tolist()

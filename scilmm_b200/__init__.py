@@ -9,4 +9,6 @@ from .SparseCholesky import (HE, MINQUE, REML, B200Factor, NotPositiveDefiniteEr
                              matrices_weighted_sum, negative_log_likelihood, run_estimates,
                              run_estimates_from_paths, simulate_vector)
 
+from .legacy import LMM, compute_HE  # noqa: F401,E402  (reference scilmm/Estimation/LMM.py:154, HE.py:22)
+
 __version__ = "0.1.0"

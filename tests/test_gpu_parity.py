@@ -399,3 +399,26 @@ def test_run_estimates_dropin(golden_c1mini, slmm):
     np.random.seed(5)
     est_o, se_o = orc.he_regression([A], covm, g["y"].copy(), compute_stderr=True)
     assert rel_err(est, est_o) < 1e-9 and rel_err(se, se_o) < 1e-7
+
+
+def test_legacy_lmm_and_compute_he_vs_reference(golden_small, slmm):
+    """scilmm_b200.legacy.LMM / compute_HE against outputs of the unmodified reference legacy modules
+    (scilmm/Estimation/LMM.py:154, HE.py:22): shared numpy probe stream, identity permutation."""
+    import os
+    import scilmm_b200
+    from tests.util import GOLDEN_DIR
+    g = golden_small
+    ref = np.load(os.path.join(GOLDEN_DIR, "case_small_legacy.npz"))
+    A, E_, H = g.csr("A"), g.csr("E"), g.csr("H")
+    cov_raw = g["cov"][:, :-1].copy()
+    for fit in (False, True):
+        coef, cc = scilmm_b200.compute_HE(g["y"].copy(), cov_raw, [A, E_, H], fit_intercept=fit)
+        assert rel_err(coef, ref["he_coef_%d" % fit]) < 1e-9
+        assert rel_err(cc, ref["he_covcoef_%d" % fit]) < 1e-9
+    chol = slmm.SparseCholesky(ordering_method="natural", rng="numpy")
+    np.random.seed(21)
+    out = scilmm_b200.LMM(chol, [A, E_], cov_raw, g["y"].copy(), with_intercept=True, reml=True, sim_num=20)
+    assert rel_err(out["covariance coefficients"], ref["lmm_sig"]) < 1e-6
+    assert rel_err(out["covariates coefficients"], ref["lmm_beta"]) < 1e-6
+    assert rel_err(out["covariance std"], ref["lmm_se"]) < 1e-5
+    assert rel_err(out["covariates p-values"], ref["lmm_pvalues"]) < 1e-5

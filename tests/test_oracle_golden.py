@@ -92,3 +92,24 @@ def test_superlu_factor_matches_dense(golden_small):
     assert abs(fs.logdet() - fd.logdet()) < 1e-11 * abs(fd.logdet())
     assert rel_err(fs.L().toarray(), fd.L().toarray()) < 1e-11
     assert np.array_equal(fs.P(), perm)
+
+
+def test_legacy_entry_points_vs_reference(golden_small):
+    """oracle restatement of scilmm/Estimation/LMM.py:154 and HE.py:22 against outputs of the unmodified reference
+    (oracle/make_golden_legacy.py -> tests/golden/case_small_legacy.npz)."""
+    import os
+    from tests.util import GOLDEN_DIR
+    g = golden_small
+    ref = np.load(os.path.join(GOLDEN_DIR, "case_small_legacy.npz"))
+    A, E, H = g.csr("A"), g.csr("E"), g.csr("H")
+    cov_raw = g["cov"][:, :-1].copy()
+    for fit in (False, True):
+        coef, cc = orc.legacy_compute_he(g["y"].copy(), cov_raw, [A, E, H], fit_intercept=fit)
+        assert rel_err(coef, ref["he_coef_%d" % fit]) < 1e-10
+        assert rel_err(cc, ref["he_covcoef_%d" % fit]) < 1e-10
+    np.random.seed(21)
+    out = orc.legacy_lmm(lambda V: DenseFactor(V), [A, E], cov_raw, g["y"].copy(), True, True, 20)
+    assert rel_err(out["covariance coefficients"], ref["lmm_sig"]) < 1e-6
+    assert rel_err(out["covariates coefficients"], ref["lmm_beta"]) < 1e-6
+    assert rel_err(out["covariance std"], ref["lmm_se"]) < 1e-5
+    assert rel_err(out["covariates p-values"], ref["lmm_pvalues"]) < 1e-5
