@@ -138,6 +138,15 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, dou
  * Profiling mode brackets every launch of the factor / solve schedules with CUDA events on the launching stream and
  * sums the time per kernel kind: 0 potrf+inverse, 1 DMMA GEMM 128x128 tiles, 2 DMMA GEMM 64x64 tiles,
  * 3 extend-add (warp per item), 4 RHS pull, 5 extend-add (CTA per item, large parents).  flops6 = dense flops issued per kind. */
+/* Two solves side by side.  Between slmm_chol_aux_begin and slmm_chol_aux_end, slmm_chol_solve / slmm_chol_lmul
+ * are issued on an auxiliary stream (ordered after everything already queued on stream 0, e.g. the
+ * factorization) instead of stream 0, so that a narrow solve (the c+1 fixed-effect columns, SparseCholesky.py:30,32)
+ * - a launch-latency-bound chain that leaves the SMs idle - overlaps the probe pipeline (:50-52) the caller issues
+ * on stream 0 next.  slmm_chol_aux_join makes stream 0 wait for the auxiliary work; the solved block must not be
+ * read (or freed) before it.  The two solves must use different RHS widths (plans are per width). */
+int slmm_chol_aux_begin(slmm_chol_t* h);
+int slmm_chol_aux_end(slmm_chol_t* h);
+int slmm_chol_aux_join(slmm_chol_t* h);
 /* raw supernodal panels (lsize doubles, layout of slmm_symbolic_arrays' sn_lptr / sn_nrow): parity tests compare
  * them supernode by supernode with the CPU oracle */
 int slmm_chol_copy_panels(slmm_chol_t* h, double* host_out);

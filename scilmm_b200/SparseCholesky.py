@@ -189,11 +189,30 @@ class RemlSession(object):
 
     def fixed_effects(self):
         """V^-1 C, chol(C'V^-1C), mu, beta, V^-1 y   (reference :29-34, one multi-RHS solve)."""
+        return self._fixed_effects_finish(self._fixed_effects_start(overlap=False))
+
+    def _fixed_effects_start(self, overlap=True):
+        """Queues the (c+1)-column solve.  With overlap=True it goes to the engine's auxiliary stream: the narrow
+        solve is a launch-latency-bound chain that leaves the SMs idle, so it runs beside the probe pipeline the
+        caller issues on stream 0 next; _fixed_effects_finish joins the two."""
         torch = self.torch
-        c = self.C.shape[1]
         B = torch.cat([self.C, self.y.unsqueeze(1)], dim=1).contiguous()
-        self.eng.solve_(B)
-        self._ViCy = B                                  # [V^-1 C | V^-1 y], kept for the fused Gram pass
+        if overlap:
+            self.eng.aux_begin()
+            try:
+                self.eng.solve_(B)
+            finally:
+                self.eng.aux_end()
+        else:
+            self.eng.solve_(B)
+        return B, overlap
+
+    def _fixed_effects_finish(self, pending):
+        B, overlap = pending
+        if overlap:
+            self.eng.aux_join()
+        c = self.C.shape[1]
+        self._ViCy = B                                  # [V^-1 C | V^-1 y], kept for the Gram pass
         ViC = B[:, :c].contiguous()
         Viy = B[:, c].contiguous()
         CtViC = (self.C.t() @ ViC).cpu().numpy()
@@ -226,20 +245,21 @@ class RemlSession(object):
         torch = self.torch
         self.factor_at(sigmas)
         logdet = self.eng.logdet()
-        ViC, chol, beta, Viy = self.fixed_effects()
-        beta_t = torch.from_numpy(beta).to("cuda")
-        Vir = Viy - ViC @ beta_t                       # V^-1 (y - C beta) by linearity
-        r = self.y - self.C @ beta_t
         n = self.n
-        nll = 0.5 * (float(r @ Vir) + n * LOG_2PI + logdet)
-        if reml:
-            nll += 0.5 * 2 * np.sum(np.log(np.diag(chol[0])))
-        # probe columns are sharded across ranks when torch.distributed is initialised
+        pending = self._fixed_effects_start()          # narrow solve on the auxiliary stream ...
+        # ... beside the probe pipeline; probe columns are sharded across ranks when torch.distributed is initialised
         rank, world = _shard.rank_world()
         if Z is None and self.functor.rng == 'numpy' and world > 1:
             Z = np.random.randn(n, sim_num)            # every rank draws the same stream, keeps its slice
         lo, hi = _shard.column_block(sim_num, rank, world)
         W = self.probes(sim_num, Z, lo, hi) if world > 1 else self.probes(sim_num, Z)
+        ViC, chol, beta, Viy = self._fixed_effects_finish(pending)
+        beta_t = torch.from_numpy(beta).to("cuda")
+        Vir = Viy - ViC @ beta_t                       # V^-1 (y - C beta) by linearity
+        r = self.y - self.C @ beta_t
+        nll = 0.5 * (float(r @ Vir) + n * LOG_2PI + logdet)
+        if reml:
+            nll += 0.5 * 2 * np.sum(np.log(np.diag(chol[0])))
         c = self.C.shape[1]
         K = self.K
         comp1 = torch.zeros(K, dtype=torch.float64, device="cuda")

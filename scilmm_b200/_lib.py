@@ -61,6 +61,9 @@ SIGNATURES = {
     "slmm_chol_lmul": (C.c_int, [vp, vp, vp, i32]),
     "slmm_chol_export_L": (C.c_int, [vp, vp, vp, vp]),
     "slmm_chol_copy_panels": (C.c_int, [vp, vp]),
+    "slmm_chol_aux_begin": (C.c_int, [vp]),
+    "slmm_chol_aux_end": (C.c_int, [vp]),
+    "slmm_chol_aux_join": (C.c_int, [vp]),
     "slmm_launch_count": (C.c_int, [C.POINTER(i64), i32]),
     "slmm_chol_set_profiling": (C.c_int, [vp, i32]),
     "slmm_chol_get_profile": (C.c_int, [vp, vp, vp, vp]),

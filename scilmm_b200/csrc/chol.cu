@@ -378,6 +378,9 @@ struct slmm_chol {
   std::vector<EntryMap> maps;
   std::map<int, std::unique_ptr<SolvePlan>> plans;
   cudaStream_t s_main = nullptr, s_bulk = nullptr;   // factorization streams (main: highest priority)
+  cudaStream_t s_aux = nullptr;        // auxiliary stream: a second solve running beside the one on stream 0
+  cudaStream_t cur = nullptr;          // stream the single-stream schedules (solves, L*Z) are issued on (0 or s_aux)
+  cudaEvent_t ev_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> events;
   bool factored = false;
@@ -467,7 +470,7 @@ static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* c
       CUDA_OK(cudaStreamWaitEvent(h->s_bulk, h->ev_fork, 0));
     }
     for (const Launch& L : sch.launches) {
-      cudaStream_t st = two ? (L.stream ? h->s_bulk : h->s_main) : (cudaStream_t)0;
+      cudaStream_t st = two ? (L.stream ? h->s_bulk : h->s_main) : h->cur;
       if (L.kind == Launch::EV_RECORD) { if (two) CUDA_OK(cudaEventRecord(h->events[L.count], st)); continue; }
       if (L.kind == Launch::EV_WAIT) { if (two) CUDA_OK(cudaStreamWaitEvent(st, h->events[L.count], 0)); continue; }
       launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs, st);
@@ -909,6 +912,8 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
     CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     CUDA_OK(cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, greatest));
     CUDA_OK(cudaStreamCreateWithPriority(&h->s_bulk, cudaStreamNonBlocking, least));
+    CUDA_OK(cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, least));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
@@ -934,6 +939,8 @@ int slmm_chol_destroy(slmm_chol_t* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->s_bulk) cudaStreamDestroy(h->s_bulk);
+  if (h->s_aux) cudaStreamDestroy(h->s_aux);
+  if (h->ev_aux) cudaEventDestroy(h->ev_aux);
   h->fact.release();
   for (auto& m : h->maps) dev_free(m.d_map);
   for (auto& kv : h->plans) kv.second->release();
@@ -1043,10 +1050,10 @@ int slmm_chol_solve(slmm_chol_t* h, double* d_B, int32_t nrhs, int32_t mode) {
   const int64_t total = (int64_t)n * nrhs;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
   // forward consumes X and leaves y in X2; backward consumes X2 and leaves x in X
-  gather_rows_kernel<<<grid, 256>>>(d_B, mode == 2 ? pl->X2 : pl->X, h->d_perm, n, nrhs, 0);
+  gather_rows_kernel<<<grid, 256, 0, h->cur>>>(d_B, mode == 2 ? pl->X2 : pl->X, h->d_perm, n, nrhs, 0);
   if (mode == 0 || mode == 1) run_schedule(h, pl->fwd, pl->X, pl->arena, pl->d_vptr, nrhs);
   if (mode == 0 || mode == 2) run_schedule(h, pl->bwd, pl->X, pl->arena, pl->d_vptr, nrhs);
-  gather_rows_kernel<<<grid, 256>>>(mode == 1 ? pl->X2 : pl->X, d_B, h->d_perm, n, nrhs, 1);
+  gather_rows_kernel<<<grid, 256, 0, h->cur>>>(mode == 1 ? pl->X2 : pl->X, d_B, h->d_perm, n, nrhs, 1);
   g_launch_count += 2;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
@@ -1060,10 +1067,10 @@ int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrh
   SolvePlan* pl = get_plan(h, nrhs);
   const int n = h->S.n;
   const int64_t total = (int64_t)n * nrhs;
-  CUDA_OK(cudaMemcpyAsync(pl->X, d_Z, total * sizeof(double), cudaMemcpyDeviceToDevice, 0));
+  CUDA_OK(cudaMemcpyAsync(pl->X, d_Z, total * sizeof(double), cudaMemcpyDeviceToDevice, h->cur));
   run_schedule(h, pl->lmul, pl->X2, pl->arena, pl->d_vptr, nrhs);
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
-  gather_rows_kernel<<<grid, 256>>>(pl->X2, d_out, h->d_perm, n, nrhs, 1);
+  gather_rows_kernel<<<grid, 256, 0, h->cur>>>(pl->X2, d_out, h->d_perm, n, nrhs, 1);
   g_launch_count++;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
@@ -1088,6 +1095,32 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* colptr, int32_t* rowidx, double*
     }
   }
   colptr[S.n] = q;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_aux_begin(slmm_chol_t* h) {
+  SLMM_TRY
+  if (!h || !h->s_aux) throw std::invalid_argument("null handle");
+  if (h->cur != nullptr) throw std::invalid_argument("auxiliary section already open");
+  CUDA_OK(cudaEventRecord(h->ev_aux, 0));               // everything issued so far (the factorization) comes first
+  CUDA_OK(cudaStreamWaitEvent(h->s_aux, h->ev_aux, 0));
+  h->cur = h->s_aux;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_aux_end(slmm_chol_t* h) {
+  if (!h) return SLMM_ERR_INVALID;
+  h->cur = nullptr;
+  return SLMM_OK;
+}
+
+int slmm_chol_aux_join(slmm_chol_t* h) {
+  SLMM_TRY
+  if (!h || !h->s_aux) throw std::invalid_argument("null handle");
+  CUDA_OK(cudaEventRecord(h->ev_aux, h->s_aux));
+  CUDA_OK(cudaStreamWaitEvent(0, h->ev_aux, 0));
   return SLMM_OK;
   SLMM_CATCH
 }

@@ -398,6 +398,15 @@ class CholEngine(object):
         check(lib().slmm_chol_lmul(self._h, Z2.data_ptr(), out.data_ptr(), int(Z2.shape[1])))
         return out if Z.dim() == 2 else out[:, 0]
 
+    def aux_begin(self):
+        check(lib().slmm_chol_aux_begin(self._h))
+
+    def aux_end(self):
+        check(lib().slmm_chol_aux_end(self._h))
+
+    def aux_join(self):
+        check(lib().slmm_chol_aux_join(self._h))
+
     def panels(self):
         """Raw supernodal panels as one host array (layout: SymbolicView.arrays() sn_lptr / sn_nrow)."""
         out = np.zeros(self.stats()["lsize"], dtype=np.float64)
