@@ -359,6 +359,25 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
   }
 }
 
+// One final reduction for ALL moments of an HE call: value j sums partial[off_j + b * stride_j] over its pass's
+// CTAs in fixed order and lands in dst[dst_j].  The descriptor table is cached on the device (it depends only on the
+// set of matrices), so a call issues its passes and this one kernel - no per-pass reductions, no small H2D copies.
+struct RedDesc { int64_t off; int32_t stride, nblocks, dst, pad; };
+__global__ void reduce_all_kernel(const double* __restrict__ partial, const RedDesc* __restrict__ desc,
+                                  double* __restrict__ dst) {
+  const RedDesc d = desc[blockIdx.x];
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < d.nblocks; b += 256) s += partial[d.off + (int64_t)b * d.stride];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && d.dst >= 0) dst[d.dst] = sh[0];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // SpMM on C-ordered blocks: out[i,:] = sum_j A[i,j] X[j,:].  A warp owns a row; lanes own columns
 // (each X row is contiguous, so every gathered row is a coalesced read).  CPL = columns per lane.
@@ -728,6 +747,22 @@ struct slmm_matset {
   double* d_y = nullptr;
   double* d_out = nullptr;
   int32_t* d_dst = nullptr;
+  // HE calls: one partial arena for all passes + the cached reduction table
+  double* he_arena = nullptr;
+  size_t he_used = 0;
+  static constexpr size_t HE_ARENA = (size_t)148 * 8 * 1024;
+  std::vector<slmm::RedDesc> he_desc, he_desc_cached;
+  slmm::RedDesc* d_he_desc = nullptr;
+  double* he_part(size_t count) {
+    if (!he_arena) he_arena = slmm::dev_alloc<double>(HE_ARENA);
+    if (he_used + count > HE_ARENA) throw std::runtime_error("HE partial arena exhausted");
+    double* p = he_arena + he_used;
+    he_used += count;
+    return p;
+  }
+  void he_add(const double* part, int nblocks, int nv, const int32_t* dst) {
+    for (int k = 0; k < nv; k++) he_desc.push_back({(int64_t)(part - he_arena) + k, nv, nblocks, dst[k], 0});
+  }
   double* partial(size_t count) {
     if (count > partial_cap) {
       dev_free(d_partial);
@@ -765,7 +800,7 @@ static void launch_group(slmm_matset* ms, const int* members, const double* d_y,
   a.indices = ms->m[members[0]].indices;
   for (int g = 0; g < G; g++) a.data[g] = ms->m[members[g]].data;
   const int grid = he_grid(r1 - r0);
-  double* part = ms->partial((size_t)grid * NV);
+  double* part = ms->he_part((size_t)grid * NV);
   he_group_kernel<G><<<grid, 256>>>(a, d_y, r0, r1, part, rend, rend ? 2.0 : 1.0);
   // destination indices inside [q_off | q_diag | S_off | S_diag]
   std::vector<int32_t> dst(NV);
@@ -777,9 +812,8 @@ static void launch_group(slmm_matset* ms, const int* members, const double* d_y,
       dst[2 * G + NP + q] = 2 * K + K * K + members[g] * K + members[h];
       q++;
     }
-  CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst.data(), NV * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
-  reduce_partials_kernel<<<NV, 256>>>(part, grid, NV, ms->d_dst, d_out);
-  g_launch_count += 2;
+  ms->he_add(part, grid, NV, dst.data());
+  g_launch_count += 1;
   // the copy above must not be overwritten by the next group before the kernel ran: d_dst is consumed in
   // stream order and the next memcpy is also stream-ordered (pageable source is staged synchronously).
 }
@@ -829,6 +863,7 @@ int slmm_matset_destroy(slmm_matset_t* ms) {
     dev_free(c.rend);
   }
   dev_free(ms->d_partial); dev_free(ms->d_y); dev_free(ms->d_out); dev_free(ms->d_dst);
+  dev_free(ms->he_arena); dev_free(ms->d_he_desc);
   for (auto& kv : ms->cross_maps) dev_free(kv.second);
   delete ms;
   return SLMM_OK;
@@ -907,6 +942,8 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
   for (int k = 0; k < K; k++)
     if (!ms->m[k].data) throw std::invalid_argument("matrix not set");
   CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * (2 * K + 2 * K * K), 0));
+  ms->he_used = 0;
+  ms->he_desc.clear();
   // Symmetric matrices (checked once per matrix on the device): every pass reads only the entries on and below
   // the diagonal and doubles the off-diagonal sums.
   bool sym_all = true;
@@ -940,13 +977,12 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
       if (gn == 1 && lead.nnz < (int64_t)8 * ms->n) {      // short rows: thread per row
         const int rows = r1 - r0;
         const int grid = std::max(1, std::min(148 * 8, (rows + 255) / 256));
-        double* part = ms->partial((size_t)grid * 4);
+        double* part = ms->he_part((size_t)grid * 4);
         he_short_kernel<<<grid, 256>>>(lead.indptr, lead.indices, lead.data, d_y, r0, r1, part, row_ends(members[g0]), off_scale);
         const int k0 = members[g0];
         const int32_t dst[4] = {k0, K + k0, 2 * K + k0 * K + k0, 2 * K + K * K + k0 * K + k0};
-        CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
-        reduce_partials_kernel<<<4, 256>>>(part, grid, 4, ms->d_dst, d_out);
-        g_launch_count += 2;
+        ms->he_add(part, grid, 4, dst);
+        g_launch_count += 1;
         continue;
       }
       switch (gn) {
@@ -975,14 +1011,13 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
           // same pattern but different chunk (groups larger than the fused pass): fall back to pairwise kernel
           for (int i : chunks[a]) for (int j : chunks[b]) {
             const int grid = he_grid(r1 - r0);
-            double* part = ms->partial((size_t)grid * 2);
+            double* part = ms->he_part((size_t)grid * 2);
             he_cross_kernel<<<grid, 256>>>(ms->m[i].indptr, ms->m[i].indices, ms->m[i].data, ms->m[j].indptr,
                                            ms->m[j].indices, ms->m[j].data, r0, r1, part);
             const int hi2 = std::max(i, j), lo2 = std::min(i, j);
             const int32_t dst[2] = {2 * K + hi2 * K + lo2, 2 * K + K * K + hi2 * K + lo2};
-            CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, 0));
-            reduce_partials_kernel<<<2, 256>>>(part, grid, 2, ms->d_dst, d_out);
-            g_launch_count += 2;
+            ms->he_add(part, grid, 2, dst);
+            g_launch_count += 1;
           }
           continue;
         }
@@ -1000,7 +1035,7 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         }
         const int64_t pn = ms->m[lp].nnz;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (pn + 255) / 256));
-        double* part = ms->partial((size_t)grid * nv);
+        double* part = ms->he_part((size_t)grid * nv);
         GroupArgs<2> pa, ta;
         pa.indptr = ms->m[P[0]].indptr; pa.indices = ms->m[P[0]].indices;
         ta.indptr = ms->m[T[0]].indptr; ta.indices = ms->m[T[0]].indices;
@@ -1022,10 +1057,21 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
             dst[(x * gt + z) * 2] = 2 * K + hi2 * K + lo2;
             dst[(x * gt + z) * 2 + 1] = 2 * K + K * K + hi2 * K + lo2;
           }
-        CUDA_OK(cudaMemcpyAsync(ms->d_dst, dst.data(), nv * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
-        reduce_partials_kernel<<<nv, 256>>>(part, grid, nv, ms->d_dst, d_out);
-        g_launch_count += 2;
+        ms->he_add(part, grid, nv, dst.data());
+        g_launch_count += 1;
       }
+  }
+  // one reduction for every moment of the call; the table is uploaded only when it changed (first call)
+  if (!ms->he_desc.empty()) {
+    const size_t nd = ms->he_desc.size();
+    if (ms->he_desc_cached.size() != nd ||
+        memcmp(ms->he_desc_cached.data(), ms->he_desc.data(), nd * sizeof(RedDesc)) != 0) {
+      dev_free(ms->d_he_desc);
+      ms->d_he_desc = dev_upload(ms->he_desc.data(), nd);
+      ms->he_desc_cached = ms->he_desc;
+    }
+    reduce_all_kernel<<<(int)nd, 256>>>(ms->he_arena, ms->d_he_desc, d_out);
+    g_launch_count++;
   }
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
