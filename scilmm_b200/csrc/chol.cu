@@ -242,7 +242,11 @@ struct PhaseBuilder {
     const bool lower = op.flags & GF_LOWER;
     const int64_t tb = (int64_t)((op.M + 127) / 128) * ((op.N + 127) / 128);
     const int64_t ts = (int64_t)((op.M + 63) / 64) * ((op.N + 63) / 64);
-    const bool small_tiles = !(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128);
+    // GF_BIGTILE: in-place ops whose N must stay inside ONE tile column (another tile of the same rows would read
+    // what this one overwrites)
+    const bool force_big = op.flags & GF_BIGTILE;
+    op.flags &= ~GF_BIGTILE;
+    const bool small_tiles = !force_big && (!(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128));
     const int64_t tiles = small_tiles ? ts : tb;
     if (!lower && tiles <= 148 && op.K >= 256 && op.C != op.A) {
       int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 64), std::max<int64_t>(1, 148 / tiles));   // one wave of CTAs
@@ -370,6 +374,8 @@ struct slmm_chol {
   double* Lx = nullptr;
   double* inv = nullptr;
   double* W = nullptr;                // inverses of the NBO-wide diagonal blocks (supernodes wider than NBI)
+  double* wscratch = nullptr;         // wide fronts: products of one recursive-doubling level
+  std::vector<int64_t> wscratch_off;
   double* arena[2] = {nullptr, nullptr};
   int64_t arena_size[2] = {0, 0};
   int* d_info = nullptr;
@@ -589,59 +595,134 @@ static OuterBlock outer_block(const slmm_chol* h, int s, int ob) {
   return b;
 }
 
+// One step of a front's factorization program.  Phase p of a level executes step p of every front of the level.
+struct FStep {
+  enum Kind { POTRF, TRSM, UPD, WINV1, WINV2, CPANEL, OUTER, SCHUR } kind;
+  int a, b;       // POTRF/TRSM/UPD: inner block index ib, -     WINV1/2: outer block, m     CPANEL: outer block, j
+};
+
 static void build_factor_schedule(slmm_chol* h) {
   const Symbolic& S = h->S;
   Schedule& sch = h->fact;
   PhaseBuilder pb, pb_rest;
   int last_bulk_ev = -1;
+  std::vector<std::vector<FStep>> prog;
   for (int d = S.nlevels - 1; d >= 0; d--) {
     add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT, 8, 0, 512);
     add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT_BIG, 4, 512);
-    int max_nib = 0;
-    for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
-      const int s = S.level_sn[q];
-      max_nib = std::max(max_nib, (S.sn_first[s + 1] - S.sn_first[s] + NBI - 1) / NBI);
-    }
-    for (int ph = 0; ph < 3 * max_nib; ph++) {
-      const int ib = ph / 3, kind = ph % 3;
-      bool outer_done = false;
-      for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
-        const int s = S.level_sn[q];
-        const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
-        const int c0 = ib * NBI;
-        if (c0 >= ns) continue;
-        const int c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
-        double* P = h->Lx + S.sn_lptr[s];
-        double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
-        const int64_t ld = ms;
-        if (kind == 0) {
-          pb.potrf.push_back({P + c0 + c0 * ld, inv, (int32_t)ld, nb, f + c0, 0});
-          sch.flops += (double)nb * nb * nb / 3.0;   // counted as nb^3/3 multiply-adds pairs
-        } else if (kind == 1) {
-          // rows below the diagonal block:  X = X * inv^T   (in place, one tile column)
-          pb.add(make_op(P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, inv, 1, NBI, ms - c1, nb, nb, 0));
-        } else {
-          const int ob0 = (c0 / NBO) * NBO, ob_end = std::min(ns, ob0 + NBO);
-          if (c1 < ob_end) {          // update the rest of the current outer block with this inner block
-            pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, ms - c1,
-                           ob_end - c1, nb, GF_LOWER | GF_ACCUM | GF_NEG));
-          } else if (c1 < ns) {       // outer block finished: update all remaining panel columns, K = block width
-            // Look-ahead: the columns of the NEXT outer block are updated on the main stream (they gate the next
-            // panel factorization); the columns beyond it go to the bulk stream and overlap with that panel
-            // factorization, whose diagonal-block steps leave almost every SM idle.
-            outer_done = true;
-            const int nx = std::min(ns, c1 + NBO);
-            const bool split = (ns - nx) >= NBO;
-            const int ncols = split ? nx - c1 : ns - c1;
-            pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, ms - c1,
-                           ncols, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
-            if (split)
-              pb_rest.add(make_op(P + nx + nx * ld, 1, ld, P + nx + ob0 * ld, 1, ld, P + nx + ob0 * ld, 1, ld, ms - nx,
-                                  ns - nx, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
-          } else if (rs > 0) {        // panel done: Schur complement  U = -L21 L21'
-            double* U = h->arena[d & 1] + h->uptr[s];
-            pb.add(make_op(U, 1, rs, P + ns, 1, ld, P + ns, 1, ld, rs, rs, ns, GF_LOWER | GF_NEG));
+    // ---- programs
+    const int nl = S.level_ptr[d + 1] - S.level_ptr[d];
+    prog.assign(nl, std::vector<FStep>());
+    size_t max_steps = 0;
+    for (int q = 0; q < nl; q++) {
+      const int s = S.level_sn[S.level_ptr[d] + q];
+      const int ns = S.sn_first[s + 1] - S.sn_first[s], ms = S.sn_nrow[s], rs = ms - ns;
+      std::vector<FStep>& pr = prog[q];
+      if (ns <= NBO) {
+        // narrow front: per 64 columns POTRF, panel solve of ALL rows below, in-block update; Schur complement last
+        const int nib = (ns + NBI - 1) / NBI;
+        for (int ib = 0; ib < nib; ib++) {
+          pr.push_back({FStep::POTRF, ib, 0});
+          pr.push_back({FStep::TRSM, ib, 0});
+          if (ib + 1 < nib) pr.push_back({FStep::UPD, ib, 0});
+        }
+        if (rs > 0) pr.push_back({FStep::SCHUR, 0, 0});
+      } else {
+        // Wide front (a dense panel chain): the 64-column steps touch ONLY the w x w diagonal block of the current
+        // outer block (tiny launches: they find free SMs at once even while bulk updates fill the machine), the
+        // block inverse W = L_D^-1 is built by recursive doubling from the 64 x 64 inverses, and the rows below take
+        // one triangular multiply L21 = A21 W' (128-column blocks, in place, last block first).
+        for (int ob = 0; ob < num_outer(ns); ob++) {
+          const int o0 = ob * NBO, o1 = std::min(ns, o0 + NBO), w = o1 - o0;
+          for (int c0 = o0; c0 < o1; c0 += NBI) {
+            const int ib = c0 / NBI;
+            pr.push_back({FStep::POTRF, ib, 0});
+            if (std::min(o1, c0 + NBI) < o1) { pr.push_back({FStep::TRSM, ib, 0}); pr.push_back({FStep::UPD, ib, 0}); }
           }
+          for (int m = NBI; m < w; m *= 2) { pr.push_back({FStep::WINV1, ob, m}); pr.push_back({FStep::WINV2, ob, m}); }
+          if (ms > o1)
+            for (int j = (w + 127) / 128 - 1; j >= 0; j--) pr.push_back({FStep::CPANEL, ob, j});
+          if (o1 < ns) pr.push_back({FStep::OUTER, ob, 0});
+          else if (rs > 0) pr.push_back({FStep::SCHUR, 0, 0});
+        }
+      }
+      max_steps = std::max(max_steps, pr.size());
+    }
+    // ---- phases
+    for (size_t ph = 0; ph < max_steps; ph++) {
+      bool outer_done = false;
+      for (int q = 0; q < nl; q++) {
+        if (ph >= prog[q].size()) continue;
+        const FStep st = prog[q][ph];
+        const int s = S.level_sn[S.level_ptr[d] + q];
+        const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
+        const bool wide = ns > NBO;
+        double* P = h->Lx + S.sn_lptr[s];
+        const int64_t ld = ms;
+        if (st.kind == FStep::POTRF || st.kind == FStep::TRSM || st.kind == FStep::UPD) {
+          const int ib = st.a, c0 = ib * NBI, c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
+          const int ob = c0 / NBO, ob0 = ob * NBO, ob_end = std::min(ns, ob0 + NBO);
+          // where the inverse of this 64 x 64 block lives: its private slot, or (wide fronts) the diagonal of W
+          double* inv = h->inv + h->invptr[s] + (int64_t)ib * NBI * NBI;
+          int64_t inv_ld = NBI;
+          if (wide) {
+            const OuterBlock wb = outer_block(h, s, ob);
+            if (wb.nbo > NBI) { inv = wb.winv + (c0 - ob0) + (int64_t)(c0 - ob0) * wb.ldw; inv_ld = wb.ldw; }
+          }
+          const int row_end = wide ? ob_end : ms;      // wide fronts: only the diagonal block of the outer block
+          if (st.kind == FStep::POTRF) {
+            pb.potrf.push_back({P + c0 + c0 * ld, inv, (int32_t)ld, nb, f + c0, (int32_t)inv_ld});
+            sch.flops += (double)nb * nb * nb / 3.0;
+          } else if (st.kind == FStep::TRSM) {
+            // rows below the diagonal block:  X = X * inv^T   (in place, one tile column)
+            pb.add(make_op(P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, inv, 1, inv_ld, row_end - c1, nb, nb, 0));
+          } else {
+            // update the rest of the current outer block with this inner block
+            pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, P + c1 + c0 * ld, 1, ld, row_end - c1,
+                           ob_end - c1, nb, GF_LOWER | GF_ACCUM | GF_NEG));
+          }
+        } else if (st.kind == FStep::WINV1 || st.kind == FStep::WINV2) {
+          // recursive doubling: inv([A 0; C B]) = [A^-1 0; -B^-1 (C A^-1)  B^-1], pairs of blocks of size m
+          const OuterBlock wb = outer_block(h, s, st.a);
+          const int m = st.b, o0 = wb.o0;
+          double* T = h->wscratch + h->wscratch_off[s];
+          int pair = 0;
+          for (int lo = 0; lo + m < wb.nbo; lo += 2 * m, pair++) {
+            const int m2 = std::min(m, wb.nbo - lo - m);
+            double* Tp = T + (int64_t)pair * m * m;
+            double* Ainv = wb.winv + lo + (int64_t)lo * wb.ldw;
+            double* Binv = wb.winv + (lo + m) + (int64_t)(lo + m) * wb.ldw;
+            double* X21 = wb.winv + (lo + m) + (int64_t)lo * wb.ldw;
+            if (st.kind == FStep::WINV1)       // T = C A^-1
+              pb.add(make_op(Tp, 1, m2, P + (o0 + lo + m) + (int64_t)(o0 + lo) * ld, 1, ld, Ainv, wb.ldw, 1, m2, m, m, 0));
+            else                               // X21 = -B^-1 T
+              pb.add(make_op(X21, 1, wb.ldw, Binv, 1, wb.ldw, Tp, m2, 1, m2, m, m2, GF_NEG));
+          }
+        } else if (st.kind == FStep::CPANEL) {
+          // rows below the outer block: L21[:, j-th 128 columns] = A21[:, 0:K) W[j-th rows, 0:K)'  (W lower triangular)
+          const OuterBlock wb = outer_block(h, s, st.a);
+          const int o0 = wb.o0, o1 = o0 + wb.nbo, j0 = 128 * st.b, nj = std::min(128, wb.nbo - j0);
+          const int K = std::min(wb.nbo, j0 + 128);
+          pb.add(make_op(P + o1 + (int64_t)(o0 + j0) * ld, 1, ld, P + o1 + (int64_t)o0 * ld, 1, ld, wb.winv + j0, 1, wb.ldw,
+                         ms - o1, nj, K, GF_BIGTILE));
+        } else if (st.kind == FStep::OUTER) {
+          // outer block finished: update all remaining panel columns, K = block width.
+          // Look-ahead: the columns of the NEXT outer block are updated on the main stream (they gate the next
+          // panel factorization); the columns beyond it go to the bulk stream and overlap with that panel
+          // factorization, whose diagonal-block steps leave almost every SM idle.
+          const int ob0 = st.a * NBO, c1 = std::min(ns, ob0 + NBO);
+          outer_done = true;
+          const int nx = std::min(ns, c1 + NBO);
+          const bool split = (ns - nx) >= NBO;
+          const int ncols = split ? nx - c1 : ns - c1;
+          pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, ms - c1,
+                         ncols, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
+          if (split)
+            pb_rest.add(make_op(P + nx + nx * ld, 1, ld, P + nx + ob0 * ld, 1, ld, P + nx + ob0 * ld, 1, ld, ms - nx,
+                                ns - nx, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
+        } else {                      // SCHUR: panel done, U = -L21 L21'
+          double* U = h->arena[d & 1] + h->uptr[s];
+          pb.add(make_op(U, 1, rs, P + ns, 1, ld, P + ns, 1, ld, rs, rs, ns, GF_LOWER | GF_NEG));
         }
       }
       if (pb_rest.empty()) {
@@ -669,16 +750,17 @@ static void build_factor_schedule(slmm_chol* h) {
     add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT, 8, 0, 512);
     add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT_BIG, 4, 512);
   }
-  // ---- batched triangular inversion of every NBO-wide diagonal block (all supernodes at once; off every front's
-  //      critical path).  W = I, then forward substitution by NBI blocks:  W[t,:] = inv_t W[t,:];
-  //      W[t+1:,:] -= L[t+1:,t] W[t,:].  The multi-RHS solves then need 2 GEMMs per 512 columns instead of per 64.
+  // ---- batched triangular inversion of the NBO-wide diagonal blocks of the NARROW fronts (64 < ns <= NBO; all
+  //      supernodes at once, off every front's critical path; wide fronts built theirs above).  W = I, then forward
+  //      substitution by NBI blocks:  W[t,:] = inv_t W[t,:];  W[t+1:,:] -= L[t+1:,t] W[t,:].  The multi-RHS solves
+  //      then need 2 GEMMs per 512 columns instead of per 64.
   if (!h->wblocks.empty()) {
     sch.launches.push_back({Launch::INIT_W, 0, (int32_t)h->wblocks.size(), (int32_t)h->wblocks.size(), 0, 0.0});
     for (int t = 0; t < NBO / NBI; t++) {
       for (int half = 0; half < 2; half++) {
         for (int s2 = 0; s2 < S.nsuper; s2++) {
           const int ns = S.sn_first[s2 + 1] - S.sn_first[s2];
-          if (ns <= NBI) continue;
+          if (ns <= NBI || ns > NBO) continue;
           double* P = h->Lx + S.sn_lptr[s2];
           const int64_t ldp = S.sn_nrow[s2];
           for (int ob = 0; ob < num_outer(ns); ob++) {
@@ -874,6 +956,8 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
   }
   h->exported_nnz = 0;
   h->wptr.assign(S.nsuper + 1, 0);
+  h->wscratch_off.assign(S.nsuper, 0);
+  int64_t wscratch_total = 0;
   for (int s = 0; s < S.nsuper; s++) {
     const int64_t ns = S.sn_first[s + 1] - S.sn_first[s], ms = S.sn_nrow[s];
     h->invptr[s + 1] = h->invptr[s] + ((ns + NBI - 1) / NBI) * NBI * NBI;
@@ -882,11 +966,13 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
     for (int ob = 0; ob < num_outer((int)ns); ob++) {
       const int nbo = (int)std::min<int64_t>(ns, (int64_t)(ob + 1) * NBO) - ob * NBO;
       if (nbo > NBI) {
-        h->wblocks.push_back({h->wptr[s] + w, nbo, 0});
+        if (ns <= NBO) h->wblocks.push_back({h->wptr[s] + w, nbo, 0});   // wide fronts build W during the factorization
         w += (int64_t)nbo * nbo;
       }
     }
     h->wptr[s + 1] = h->wptr[s] + w;
+    h->wscratch_off[s] = wscratch_total;
+    if (ns > NBO) wscratch_total += (int64_t)(NBO / 2) * (NBO / 2);       // C A^-1 products of one doubling level
   }
   h->d_sn_first = dev_upload(S.sn_first.data(), S.sn_first.size());
   h->d_sn_nrow = dev_upload(S.sn_nrow.data(), S.sn_nrow.size());
@@ -902,6 +988,8 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
   h->Lx = dev_alloc<double>(S.lsize);
   h->inv = dev_alloc<double>(h->invptr[S.nsuper]);
   h->W = dev_alloc<double>(h->wptr[S.nsuper]);
+  CUDA_OK(cudaMemset(h->W, 0, std::max<int64_t>(1, h->wptr[S.nsuper]) * sizeof(double)));   // upper blocks of wide fronts' W stay zero
+  h->wscratch = dev_alloc<double>(wscratch_total);
   h->d_wblocks = dev_upload(h->wblocks.data(), h->wblocks.size());
   h->arena[0] = dev_alloc<double>(h->arena_size[0]);
   h->arena[1] = dev_alloc<double>(h->arena_size[1]);
@@ -932,7 +1020,7 @@ int slmm_chol_destroy(slmm_chol_t* h) {
   dev_free(h->d_sn_first); dev_free(h->d_sn_nrow); dev_free(h->d_rows); dev_free(h->d_rel);
   dev_free(h->d_child_ptr); dev_free(h->d_child_idx); dev_free(h->d_col2sn); dev_free(h->d_perm);
   dev_free(h->d_sn_rowptr); dev_free(h->d_sn_lptr); dev_free(h->d_sn_uptr);
-  dev_free(h->Lx); dev_free(h->inv); dev_free(h->W); dev_free(h->d_wblocks); dev_free(h->arena[0]); dev_free(h->arena[1]);
+  dev_free(h->Lx); dev_free(h->inv); dev_free(h->W); dev_free(h->wscratch); dev_free(h->d_wblocks); dev_free(h->arena[0]); dev_free(h->arena[1]);
   dev_free(h->d_info); dev_free(h->d_partial);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

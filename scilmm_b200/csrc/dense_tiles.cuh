@@ -18,7 +18,8 @@ namespace slmm {
 constexpr int NBI = 64;   // diagonal block size (POTRF / inverse granularity)
 constexpr int POTRF_SMEM = 2 * NBI * (NBI + 1) * 8;
 
-enum GemmFlags { GF_LOWER = 1, GF_ACCUM = 2, GF_NEG = 4, GF_WS = 8 /* C is an offset into the split-K workspace */ };
+enum GemmFlags { GF_LOWER = 1, GF_ACCUM = 2, GF_NEG = 4, GF_WS = 8 /* C is an offset into the split-K workspace */,
+                 GF_BIGTILE = 16 /* host-side only: keep the 128 x 128 tile configuration */ };
 
 struct GemmOp {
   double* C;
@@ -45,7 +46,7 @@ struct PotrfOp {
   double* inv;      // NBI x NBI column-major slot for the inverse of the factored block
   int32_t ld, nb;
   int32_t colbase;  // global (permuted) index of the first column, for failure reporting
-  int32_t pad;
+  int32_t inv_ld;   // leading dimension of the inverse slot (NBI for the private slots, wider inside a block inverse)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(const PotrfOp* __restric
   for (int q = tid; q < NBI * NBI; q += 256) {
     const int i = q % NBI, jj = q / NBI;
     if (i < nb && jj < nb && i >= jj) op.blk[i + (int64_t)jj * op.ld] = Lf[i][jj];
-    op.inv[i + jj * NBI] = (i < nb && jj < nb) ? X[i][jj] : 0.0;
+    // a private 64 x 64 slot is padded with zeros; inside a wider block inverse only the nb x nb part exists
+    if (op.inv_ld == NBI || (i < nb && jj < nb)) op.inv[i + (int64_t)jj * op.inv_ld] = (i < nb && jj < nb) ? X[i][jj] : 0.0;
   }
 }
 

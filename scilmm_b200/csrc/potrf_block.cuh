@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel_v3(const PotrfOp* __rest
   for (int q = tid; q < NBI * NBI; q += 256) {
     const int i = q % NBI, jj = q / NBI;
     if (i < nb && jj < nb && i >= jj) op.blk[i + (int64_t)jj * op.ld] = Lf[i][jj];
-    op.inv[i + jj * NBI] = (i < nb && jj < nb) ? X[i][jj] : 0.0;
+    op.inv[i + (int64_t)jj * op.inv_ld] = (i < nb && jj < nb) ? X[i][jj] : 0.0;
   }
   PDBG(4)
 }

@@ -36,7 +36,7 @@ int main() {
     double *d_a, *d_inv; PotrfOp* d_ops; int* d_info;
     cudaMalloc(&d_a, h.size() * 8); cudaMalloc(&d_inv, (size_t)nblk * 4096 * 8); cudaMalloc(&d_ops, nblk * sizeof(PotrfOp)); cudaMalloc(&d_info, 4);
     std::vector<PotrfOp> ops(nblk);
-    for (int b = 0; b < nblk; b++) ops[b] = {d_a + (size_t)b * ld * 64, d_inv + (size_t)b * 4096, ld, nb, b * 64, 0};
+    for (int b = 0; b < nblk; b++) ops[b] = {d_a + (size_t)b * ld * 64, d_inv + (size_t)b * 4096, ld, nb, b * 64, 64};
     cudaMemcpy(d_ops, ops.data(), nblk * sizeof(PotrfOp), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
     cudaFuncSetAttribute(potrf_inv_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF3_SMEM);
