@@ -17,6 +17,7 @@
 
 #include "common.h"
 #include "dense_tiles.cuh"
+#include "potrf_block.cuh"
 #include "symbolic.h"
 
 namespace slmm {
@@ -412,7 +413,7 @@ static void init_kernel_attributes() {
   if (done) return;
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
-  CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF4_SMEM));
   done = true;
 }
 
@@ -420,7 +421,7 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
                        double* const* vec_arena, const int64_t* d_vptr, int nrhs, cudaStream_t st) {
   switch (L.kind) {
     case Launch::POTRF:
-      potrf_inv_kernel<<<L.grid, 256, POTRF_SMEM, st>>>(sch.d_potrf + L.off, h->d_info);
+      potrf_inv_kernel_v4<<<L.grid, 256, POTRF4_SMEM, st>>>(sch.d_potrf + L.off, h->d_info);
       break;
     case Launch::GEMM_BIG:
       gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM, st>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);

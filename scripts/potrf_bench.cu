@@ -39,7 +39,7 @@ int main() {
     for (int b = 0; b < nblk; b++) ops[b] = {d_a + (size_t)b * ld * 64, d_inv + (size_t)b * 4096, ld, nb, b * 64, 64};
     cudaMemcpy(d_ops, ops.data(), nblk * sizeof(PotrfOp), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
-    cudaFuncSetAttribute(potrf_inv_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF3_SMEM);
+    cudaFuncSetAttribute(potrf_inv_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF4_SMEM);
     for (int ver = 1; ver <= 2; ver++) {
       for (int grid : {1, nblk}) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -49,7 +49,7 @@ int main() {
           int big = 0x7fffffff; cudaMemcpy(d_info, &big, 4, cudaMemcpyHostToDevice);
           cudaEventRecord(e0);
           if (ver == 1) potrf_inv_kernel<<<grid, 256, POTRF_SMEM>>>(d_ops, d_info);
-          else potrf_inv_kernel_v3<<<grid, 256, POTRF3_SMEM>>>(d_ops, d_info);
+          else potrf_inv_kernel_v4<<<grid, 256, POTRF4_SMEM>>>(d_ops, d_info);
           cudaEventRecord(e1); cudaEventSynchronize(e1);
           float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
         }
@@ -73,7 +73,7 @@ int main() {
     h[3 + 3 * ld] = -1.0;
     cudaMemcpy(d_a, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
     int big = 0x7fffffff; cudaMemcpy(d_info, &big, 4, cudaMemcpyHostToDevice);
-    potrf_inv_kernel_v3<<<1, 256, POTRF3_SMEM>>>(d_ops, d_info);
+    potrf_inv_kernel_v4<<<1, 256, POTRF4_SMEM>>>(d_ops, d_info);
     int info; cudaMemcpy(&info, d_info, 4, cudaMemcpyDeviceToHost);
     printf("nb=%2d v2 non-PD at column 3 -> info %d (expect 4)\n", nb, info);
     cudaFree(d_a); cudaFree(d_inv); cudaFree(d_ops); cudaFree(d_info);
