@@ -605,8 +605,8 @@ struct FStep {
 static void build_factor_schedule(slmm_chol* h) {
   const Symbolic& S = h->S;
   Schedule& sch = h->fact;
-  PhaseBuilder pb, pb_rest;
-  int last_bulk_ev = -1;
+  PhaseBuilder pb, pb_rest, pb_unrest;
+  int last_bulk_ev = -1, unrest_ev = -1;
   std::vector<std::vector<FStep>> prog;
   for (int d = S.nlevels - 1; d >= 0; d--) {
     add_pull_items(sch, S, h->uptr, d, 0, Launch::PULL_MAT, 8, 0, 512);
@@ -651,10 +651,11 @@ static void build_factor_schedule(slmm_chol* h) {
     }
     // ---- phases
     for (size_t ph = 0; ph < max_steps; ph++) {
-      bool outer_done = false;
+      bool outer_done = false, needs_below = false;
       for (int q = 0; q < nl; q++) {
         if (ph >= prog[q].size()) continue;
         const FStep st = prog[q][ph];
+        if (st.kind == FStep::CPANEL || st.kind == FStep::SCHUR) needs_below = true;
         const int s = S.level_sn[S.level_ptr[d] + q];
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
         const bool wide = ns > NBO;
@@ -716,8 +717,15 @@ static void build_factor_schedule(slmm_chol* h) {
           const int nx = std::min(ns, c1 + NBO);
           const bool split = (ns - nx) >= NBO;
           const int ncols = split ? nx - c1 : ns - c1;
-          pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, ms - c1,
+          // Of the next block's columns only the square diagonal part gates the chain (the 64-column steps of the
+          // next outer block); the rows below it are needed when that block's triangular panel multiply starts, so
+          // they go to the bulk stream with their own event.
+          const int below = ms - c1 - ncols;
+          pb.add(make_op(P + c1 + c1 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld, ncols,
                          ncols, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
+          if (below > 0)
+            pb_unrest.add(make_op(P + (c1 + ncols) + c1 * ld, 1, ld, P + (c1 + ncols) + ob0 * ld, 1, ld, P + c1 + ob0 * ld, 1, ld,
+                                  below, ncols, c1 - ob0, GF_ACCUM | GF_NEG));
           if (split)
             pb_rest.add(make_op(P + nx + nx * ld, 1, ld, P + nx + ob0 * ld, 1, ld, P + nx + ob0 * ld, 1, ld, ms - nx,
                                 ns - nx, c1 - ob0, GF_LOWER | GF_ACCUM | GF_NEG));
@@ -726,28 +734,41 @@ static void build_factor_schedule(slmm_chol* h) {
           pb.add(make_op(U, 1, rs, P + ns, 1, ld, P + ns, 1, ld, rs, rs, ns, GF_LOWER | GF_NEG));
         }
       }
-      if (pb_rest.empty()) {
-        // an unsplit trailing update still writes columns the previous bulk update may be writing
-        if (outer_done && last_bulk_ev >= 0) {
-          sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
-          last_bulk_ev = -1;
-        }
-        pb.flush(sch);
-      } else {
-        const int ev_panel = sch.nevents++, ev_rest = sch.nevents++;
-        sch.launches.push_back({Launch::EV_RECORD, 0, ev_panel, 0, 0, 0.0, 0, 0});    // panels of this block are final
-        if (last_bulk_ev >= 0) sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
-        pb.flush(sch, 0);                                                             // next-panel updates (+ other fronts)
+      const bool side = !pb_rest.empty() || !pb_unrest.empty();
+      int ev_panel = -1;
+      if (side) {                     // the panels of this outer block are final from here on
+        ev_panel = sch.nevents++;
+        sch.launches.push_back({Launch::EV_RECORD, 0, ev_panel, 0, 0, 0.0, 0, 0});
+      }
+      // a trailing update writes entries the previous bulk updates may still be writing
+      if (outer_done && last_bulk_ev >= 0) {
+        sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
+        last_bulk_ev = -1;
+      }
+      // the triangular panel multiply (and the Schur complement) read rows the bulk stream updated
+      if (needs_below && unrest_ev >= 0) {
+        sch.launches.push_back({Launch::EV_WAIT, 0, unrest_ev, 0, 0, 0.0, 0, 0});
+        unrest_ev = -1;
+      }
+      pb.flush(sch, 0);               // critical chain (+ the steps of every other front)
+      if (side) {
         sch.launches.push_back({Launch::EV_WAIT, 0, ev_panel, 0, 0, 0.0, 0, 1});
-        pb_rest.flush(sch, 1);
-        sch.launches.push_back({Launch::EV_RECORD, 0, ev_rest, 0, 0, 0.0, 0, 1});
-        last_bulk_ev = ev_rest;
+        if (!pb_unrest.empty()) {     // rows below the next block first, with their own event
+          pb_unrest.flush(sch, 1);
+          unrest_ev = sch.nevents++;
+          sch.launches.push_back({Launch::EV_RECORD, 0, unrest_ev, 0, 0, 0.0, 0, 1});
+          last_bulk_ev = unrest_ev;
+        }
+        if (!pb_rest.empty()) {
+          pb_rest.flush(sch, 1);
+          last_bulk_ev = sch.nevents++;
+          sch.launches.push_back({Launch::EV_RECORD, 0, last_bulk_ev, 0, 0, 0.0, 0, 1});
+        }
       }
     }
-    if (last_bulk_ev >= 0) {        // level boundary: everything of this level is complete before the pulls
-      sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
-      last_bulk_ev = -1;
-    }
+    // level boundary: everything of this level is complete before the pulls
+    if (last_bulk_ev >= 0) sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
+    last_bulk_ev = unrest_ev = -1;
     add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT, 8, 0, 512);
     add_pull_items(sch, S, h->uptr, d, 1, Launch::PULL_MAT_BIG, 4, 512);
   }
