@@ -361,7 +361,10 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_tiles_kernel<128,128> (FP64 DMMA)", "achieved": round(achieved, 3),
                 "peak": round(dgemm_tflops, 3), "unit": "TFLOP/s", "frac": round(achieved / dgemm_tflops, 4),
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "traffic": None, "launches": gb["launches"], "kernel_ms_per_factorization": round(gb["ms"], 2),
+                # dram__bytes_read + write of ONE representative launch (ncu --set full): 16384 x 16384 lower-masked
+                # trailing update, K = 512 (4.6 ms, 2.06e11 flop) - profiles/r01_gemm_big_lower_K512_ncu.txt
+                "traffic": 1.7347e9, "traffic_launch": "M=N=16384 lower, K=512: 0.70 GB read + 1.03 GB written",
+                "launches": gb["launches"], "kernel_ms_per_factorization": round(gb["ms"], 2),
                 "share_of_factorization": round(gb["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())), 3)}
     peaks = measured_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
@@ -504,7 +507,10 @@ def bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks):
     out = {"workload": "HE fit, simulated pedigree %d (sf=%g), K=3 (IBD, AoA, household)" % (args.he_n, args.he_sf),
            **info, "nnz_household": int(H.nnz), "n_gpus": world, "device_ms": round(dev_ms, 4),
            "e2e_s": round(e2e_s, 3), "h2d_bytes": int(ms.h2d_bytes + 8 * n), "estimates": [float(v) for v in est],
-           "roofline": {"bound": "hbm", "kernel": "he_group_kernel<2> + he_group_kernel<1> + he_cross_kernel x2",
+           "roofline": {"bound": "hbm", "kernel": "he_group_kernel<2> (IBD + AoA, lower triangle) + he_short_kernel (household) + "
+                                  "he_cross_mapped_kernel<1,2> + reduce_all_kernel",
+                        "bytes_formula": "SURVEY 8d: sum_k 12 nnz_k + 4(n+1) per pattern (8 nnz for a matrix sharing a "
+                                         "pattern) + 3*8n; the symmetric traversal reads about half of it from DRAM",
                         "achieved": round(alg_bytes / dev_ms / 1e6, 1), "peak": hbm * world, "unit": "GB/s",
                         "frac": round(alg_bytes / dev_ms / 1e6 / (hbm * world), 4), "algorithmic_bytes": alg_bytes}}
     if not args.skip_cpu and rank == 0 and world == 1:
