@@ -1,7 +1,7 @@
 // Diagonal-block Cholesky + triangular inverse on FP64 tensor cores (v4).  One CTA (256 threads) per block <= 64 x 64.
 //
-// The register-blocked kernel (dense_tiles.cuh, potrf_inv_kernel) spends ~300 instructions per thread and column:
-// it is bound by instruction issue, 55 us per block, and sits on the critical chain of every wide front.  Here the
+// The register-blocked predecessor (scripts/potrf_v1_baseline.cuh) spent ~300 instructions per thread and column:
+// it was bound by instruction issue, 55 us per block, on the critical chain of every wide front.  Here the
 // block is factored 8 columns at a time:
 //   (a) warp 0 factors the 8 x 8 diagonal sub-block in registers (lane i = row i, pivots / columns by shuffle) and
 //       inverts it (lane c = column c);

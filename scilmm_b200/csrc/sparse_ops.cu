@@ -205,80 +205,6 @@ __global__ void __launch_bounds__(256) he_short_kernel(const int32_t* __restrict
   }
 }
 
-// Hadamard dot where one matrix has short rows: thread per row of the short matrix, binary search in the other.
-__global__ void __launch_bounds__(256) he_cross_short_kernel(const int32_t* __restrict__ sp_, const int32_t* __restrict__ si,
-                                                             const double* __restrict__ sx, const int32_t* __restrict__ lp,
-                                                             const int32_t* __restrict__ li, const double* __restrict__ lx,
-                                                             int row_begin, int row_end, double* __restrict__ partial) {
-  double off = 0.0, dg = 0.0;
-  for (int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += gridDim.x * blockDim.x) {
-    const int sb = sp_[row], se = sp_[row + 1], lb = lp[row], le = lp[row + 1];
-    for (int p = sb; p < se; p++) {
-      const int col = si[p];
-      int lo = lb, hi = le;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (li[mid] < col) lo = mid + 1; else hi = mid; }
-      if (lo < le && li[lo] == col) {
-        const double v = sx[p] * lx[lo];
-        if (col == row) dg += v; else off += v;
-      }
-    }
-  }
-  __shared__ double sh[8][2];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  off = warp_sum(off);
-  dg = warp_sum(dg);
-  if (lane == 0) { sh[warp][0] = off; sh[warp][1] = dg; }
-  __syncthreads();
-  if (threadIdx.x < 2) {
-    double s2 = 0.0;
-    for (int w = 0; w < 8; w++) s2 += sh[w][threadIdx.x];
-    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s2;
-  }
-}
-
-// Hadamard dots between two pattern groups in one pass: every entry of the probe pattern is located once in the
-// target pattern (sorted rows, binary search) and multiplied with all GP x GT value pairs.
-// TPR = true: thread per probe row (short rows), false: warp per probe row.  partial: [GP*GT][off, diag] per CTA.
-template <int GP, int GT, bool TPR>
-__global__ void __launch_bounds__(256) he_cross_multi_kernel(GroupArgs<GP> pr, GroupArgs<GT> tg, int row_begin,
-                                                             int row_end, double* __restrict__ partial,
-                                                             const int32_t* __restrict__ rend, double off_scale) {
-  constexpr int NV = GP * GT * 2;
-  double acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; k++) acc[k] = 0.0;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  const int first = TPR ? gtid : (gtid >> 5), step = TPR ? gthreads : (gthreads >> 5);
-  for (int row = row_begin + first; row < row_end; row += step) {
-    const int sb = pr.indptr[row], se = rend ? rend[row] : pr.indptr[row + 1], lb = tg.indptr[row], le = tg.indptr[row + 1];
-    for (int p = sb + (TPR ? 0 : lane); p < se; p += (TPR ? 1 : 32)) {
-      const int col = pr.indices[p];
-      int lo = lb, hi = le;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (tg.indices[mid] < col) lo = mid + 1; else hi = mid; }
-      if (lo < le && tg.indices[lo] == col) {
-        const int d = col == row ? 1 : 0;
-#pragma unroll
-        for (int gp = 0; gp < GP; gp++)
-#pragma unroll
-          for (int gt = 0; gt < GT; gt++) acc[(gp * GT + gt) * 2 + d] += pr.data[gp][p] * tg.data[gt][lo];
-      }
-    }
-  }
-  __shared__ double sh[8][NV];
-#pragma unroll
-  for (int k = 0; k < NV; k++) {
-    const double v = warp_sum(acc[k]) * ((k & 1) ? 1.0 : off_scale);     // even slots: off-diagonal sums
-    if (lane == 0) sh[warp][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    double s2 = 0.0;
-    for (int w = 0; w < 8; w++) s2 += sh[w][threadIdx.x];
-    partial[(int64_t)blockIdx.x * NV + threadIdx.x] = s2;
-  }
-}
-
 // Position map of one pattern inside another (built once per pattern pair and cached: patterns do not change
 // between HE calls): map[p] = 2 * (position of probe entry p in the target's arrays) + (1 if diagonal), or -1
 // when the target has no such entry (or, for symmetric sets, when the entry lies above the diagonal).

@@ -1,12 +1,13 @@
-// Developer harness: diagonal-block Cholesky + inverse kernels (v1 register-blocked vs v2 16x16-blocked),
+// Developer harness: diagonal-block Cholesky + inverse kernels (v1 register-blocked vs v4 DMMA-blocked),
 // correctness against a host reference and latency (1 block) / throughput (many blocks).
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I scilmm_b200/csrc scripts/potrf_bench.cu -o scripts/potrf_bench.bin
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I scilmm_b200/csrc -I scripts scripts/potrf_bench.cu -o scripts/potrf_bench.bin
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #define POTRF_DEBUG
 #include "potrf_block.cuh"
+#include "potrf_v1_baseline.cuh"
 using namespace slmm;
 
 static void host_chol(std::vector<double>& a, int n, int ld) {
