@@ -249,7 +249,7 @@ struct PhaseBuilder {
     op.flags &= ~GF_BIGTILE;
     const bool small_tiles = !force_big && (!(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128));
     const int64_t tiles = small_tiles ? ts : tb;
-    if (!lower && tiles <= 148 && op.K >= 256 && op.C != op.A) {
+    if (!lower && !(op.flags & GF_TRIL_B) && tiles <= 148 && op.K >= 256 && op.C != op.A) {
       int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 64), std::max<int64_t>(1, 148 / tiles));   // one wave of CTAs
       const int kc = S > 0 ? (((op.K + S - 1) / S) + 15) / 16 * 16 : op.K;
       S = (op.K + kc - 1) / kc;
@@ -298,6 +298,7 @@ struct PhaseBuilder {
         op.tile_start = (int32_t)tiles;
         tiles += (int64_t)op.tiles_m * op.tiles_n;
         double f = 2.0 * op.M * op.N * op.K;
+        if (op.flags & GF_TRIL_B) f = (double)op.M * op.N * op.K;      // about half of K per output column
         if (op.flags & GF_LOWER) {       // entries on/below the diagonal of an M x N region (M >= N)
           const double nn = std::min(op.M, op.N);
           f = 2.0 * op.K * ((double)op.M * op.N - nn * (nn - 1) / 2.0);
@@ -919,7 +920,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
       double* P = h->Lx + S.sn_lptr[s];
       const int64_t ld = ms;
       // out_top = L11 z_top (upper part of the diagonal block is stored as zeros)
-      pb.add(make_op(pl->X2 + (int64_t)f * R, 1, R, pl->X + (int64_t)f * R, 1, R, P, 1, ld, nrhs, ns, ns, 0));
+      pb.add(make_op(pl->X2 + (int64_t)f * R, 1, R, pl->X + (int64_t)f * R, 1, R, P, 1, ld, nrhs, ns, ns, GF_TRIL_B));
       if (rs > 0)
         pb.add(make_op(pl->arena[d & 1] + vptr[s], 1, R, pl->X + (int64_t)f * R, 1, R, P + ns, 1, ld, nrhs, rs, ns, 0));
     }

@@ -18,7 +18,8 @@ namespace slmm {
 constexpr int NBI = 64;   // diagonal block size (POTRF / inverse granularity)
 
 enum GemmFlags { GF_LOWER = 1, GF_ACCUM = 2, GF_NEG = 4, GF_WS = 8 /* C is an offset into the split-K workspace */,
-                 GF_BIGTILE = 16 /* host-side only: keep the 128 x 128 tile configuration */ };
+                 GF_BIGTILE = 16 /* host-side only: keep the 128 x 128 tile configuration */,
+                 GF_TRIL_B = 32 /* B(j,k) = 0 for k > j (lower-triangular B): a tile stops at k = tn0 + TN */ };
 
 struct GemmOp {
   double* C;
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(c
   if ((flags & GF_LOWER) && tm0 + TM <= tn0) return;   // tile entirely above the diagonal (whole CTA exits)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int M = op.M, N = op.N, K = op.K;
+  const int M = op.M, N = op.N;
+  const int K = (flags & GF_TRIL_B) ? min(op.K, tn0 + TN) : op.K;   // triangular B: the rest of K multiplies zeros
   const int nslab = (K + KS - 1) / KS;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 32 * NPW); mbar_init(empty_bar + s, NCW); }
