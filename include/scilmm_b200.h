@@ -121,6 +121,10 @@ int slmm_chol_register_pattern(slmm_chol_t* h, const int32_t* h_indptr, const in
  * supernodal panels:  panels = 0 ; panels += sigma * values  for each call, in call order (rounded multiply then
  * rounded add, the order scipy uses).  first != 0 clears the panels before adding. */
 int slmm_chol_add_values(slmm_chol_t* h, int32_t map_id, const double* d_values, double sigma, int32_t first);
+/* Same for two matrices sharing one registered pattern (A and A o A): V += sigma0*A0 + sigma1*A1 in one pass over
+ * the scatter map, rounded exactly like two consecutive slmm_chol_add_values calls. */
+int slmm_chol_add_values2(slmm_chol_t* h, int32_t map_id, const double* d_values0, double sigma0,
+                          const double* d_values1, double sigma1, int32_t first);
 /* numeric supernodal LL' (the factorize half of sksparse.cholmod.cholesky).  On a non-positive pivot returns
  * SLMM_ERR_NOT_POSDEF and *fail_col = failing column in permuted order. */
 int slmm_chol_factorize(slmm_chol_t* h, int32_t* fail_col);

@@ -182,8 +182,15 @@ class RemlSession(object):
 
     # K1 + K2
     def factor_at(self, sigmas):
-        for k in range(self.K):
-            self.eng.add_values(self.map_ids[k], self.matset.values_ptr(k), float(sigmas[k]), k == 0)
+        k = 0
+        while k < self.K:      # consecutive matrices with one pattern (A, A o A) are scattered in one pass
+            if k + 1 < self.K and self.map_ids[k + 1] == self.map_ids[k]:
+                self.eng.add_values2(self.map_ids[k], self.matset.values_ptr(k), float(sigmas[k]),
+                                     self.matset.values_ptr(k + 1), float(sigmas[k + 1]), k == 0)
+                k += 2
+            else:
+                self.eng.add_values(self.map_ids[k], self.matset.values_ptr(k), float(sigmas[k]), k == 0)
+                k += 1
         self.eng.factorize()
         return B200Factor(self.eng)
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "slmm_chol_perm": (C.c_int, [vp, vp]),
     "slmm_chol_register_pattern": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
     "slmm_chol_add_values": (C.c_int, [vp, i32, vp, f64, i32]),
+    "slmm_chol_add_values2": (C.c_int, [vp, i32, vp, f64, vp, f64, i32]),
     "slmm_chol_factorize": (C.c_int, [vp, C.POINTER(i32)]),
     "slmm_chol_logdet": (C.c_int, [vp, C.POINTER(f64)]),
     "slmm_chol_solve": (C.c_int, [vp, vp, i32, i32]),

@@ -53,6 +53,18 @@ __global__ void scatter_axpy_kernel(const int64_t* __restrict__ map, const doubl
   }
 }
 
+// two matrices that share one sparsity pattern (IBD and its Hadamard square) in one pass: the scatter map and the
+// targets are read / read-modify-written once; the rounding sequence is the one of two consecutive passes
+__global__ void scatter_axpy2_kernel(const int64_t* __restrict__ map, const double* __restrict__ v0, double s0,
+                                     const double* __restrict__ v1, double s1, double* __restrict__ Lx, int64_t nnz) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < nnz; e += stride) {
+    const int64_t tgt = map[e];
+    if (tgt >= 0) Lx[tgt] = __dadd_rn(__dadd_rn(Lx[tgt], __dmul_rn(s0, v0[e])), __dmul_rn(s1, v1[e]));
+  }
+}
+
 __device__ __forceinline__ int lower_bound_dev(const int32_t* a, int n, int v) {
   int lo = 0, hi = n;
   while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
@@ -1109,6 +1121,23 @@ int slmm_chol_add_values(slmm_chol_t* h, int32_t map_id, const double* d_values,
   if (m.nnz > 0) {
     const int grid = (int)std::min<int64_t>((m.nnz + 255) / 256, 148 * 16);
     scatter_axpy_kernel<<<grid, 256>>>(m.d_map, d_values, sigma, h->Lx, m.nnz);
+    g_launch_count++;
+  }
+  CUDA_OK(cudaGetLastError());
+  h->factored = false;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_add_values2(slmm_chol_t* h, int32_t map_id, const double* d_values0, double sigma0,
+                          const double* d_values1, double sigma1, int32_t first) {
+  SLMM_TRY
+  if (!h || map_id < 0 || map_id >= (int)h->maps.size() || !d_values0 || !d_values1) throw std::invalid_argument("bad arguments");
+  if (first) CUDA_OK(cudaMemsetAsync(h->Lx, 0, h->S.lsize * sizeof(double), 0));
+  const EntryMap& m = h->maps[map_id];
+  if (m.nnz > 0) {
+    const int grid = (int)std::min<int64_t>((m.nnz + 255) / 256, 148 * 16);
+    scatter_axpy2_kernel<<<grid, 256>>>(m.d_map, d_values0, sigma0, d_values1, sigma1, h->Lx, m.nnz);
     g_launch_count++;
   }
   CUDA_OK(cudaGetLastError());

@@ -372,6 +372,10 @@ class CholEngine(object):
     def add_values(self, map_id, values_ptr, sigma, first):
         check(lib().slmm_chol_add_values(self._h, int(map_id), values_ptr, float(sigma), 1 if first else 0))
 
+    def add_values2(self, map_id, values_ptr0, sigma0, values_ptr1, sigma1, first):
+        check(lib().slmm_chol_add_values2(self._h, int(map_id), values_ptr0, float(sigma0), values_ptr1, float(sigma1),
+                                          1 if first else 0))
+
     def factorize(self):
         col = C.c_int32(-1)
         code = lib().slmm_chol_factorize(self._h, C.byref(col))
