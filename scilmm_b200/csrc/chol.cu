@@ -244,6 +244,7 @@ struct PhaseBuilder {
   std::vector<PotrfOp> potrf;
   std::vector<ReduceOp> reduces;
   int64_t ws_used = 0;
+  bool allow_split = true;    // builders whose launches run beside another builder's must not share the split-K workspace
   void push(const GemmOp& op, bool small_tiles) {
     if (small_tiles) small.push_back(op); else big.push_back(op);
   }
@@ -261,7 +262,7 @@ struct PhaseBuilder {
     op.flags &= ~GF_BIGTILE;
     const bool small_tiles = !force_big && (!(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128));
     const int64_t tiles = small_tiles ? ts : tb;
-    if (!lower && !(op.flags & GF_TRIL_B) && tiles <= 148 && op.K >= 256 && op.C != op.A) {
+    if (allow_split && !lower && !(op.flags & GF_TRIL_B) && tiles <= 148 && op.K >= 256 && op.C != op.A) {
       int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 64), std::max<int64_t>(1, 148 / tiles));   // one wave of CTAs
       const int kc = S > 0 ? (((op.K + S - 1) / S) + 15) / 16 * 16 : op.K;
       S = (op.K + kc - 1) / kc;
@@ -478,7 +479,9 @@ static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* c
   const DevSym ds = h->devsym();
   int64_t nk = 0;
   if (!h->profiling) {
-    const bool two = sch.nevents > 0 && h->s_main != nullptr;
+    // schedules with events run on the priority + bulk stream pair; inside an auxiliary section (cur != 0) the
+    // pair may already be in use by the solve on stream 0, so the list is walked serially (a valid order)
+    const bool two = sch.nevents > 0 && h->s_main != nullptr && h->cur == nullptr;
     if (two) {
       while ((int)h->events.size() < sch.nevents) {
         cudaEvent_t e;
@@ -619,6 +622,7 @@ static void build_factor_schedule(slmm_chol* h) {
   const Symbolic& S = h->S;
   Schedule& sch = h->fact;
   PhaseBuilder pb, pb_rest, pb_unrest;
+  pb_rest.allow_split = pb_unrest.allow_split = false;   // bulk-stream ops run beside the chain: the split-K workspace has one user
   int last_bulk_ev = -1, unrest_ev = -1;
   std::vector<std::vector<FStep>> prog;
   for (int d = S.nlevels - 1; d >= 0; d--) {
@@ -848,7 +852,30 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
   pl->d_vptr = dev_upload(vptr.data(), vptr.size());
   pl->bytes = ((size_t)2 * n * nrhs + asz[0] + asz[1]) * 8;
   const int64_t R = nrhs;
-  PhaseBuilder pb;
+  PhaseBuilder pb, pb_rest;
+  pb_rest.allow_split = false;           // bulk-stream ops run beside the chain: one workspace, one user
+  const bool lookahead = nrhs >= 64;     // narrow solves are launch-latency chains: nothing to overlap with
+  int last_bulk_ev = -1;
+  // One phase: the chain's launches on the main stream; look-ahead remainders (if any) on the bulk stream, after
+  // the diagonal step that produced their operand and before anything that touches the same rows again.
+  auto flush_pair = [&](Schedule& sch, bool updated) {
+    int ev_diag = -1;
+    if (!pb_rest.empty()) {
+      ev_diag = sch.nevents++;
+      sch.launches.push_back({Launch::EV_RECORD, 0, ev_diag, 0, 0, 0.0, 0, 0});
+    }
+    if (updated && last_bulk_ev >= 0) {
+      sch.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0});
+      last_bulk_ev = -1;
+    }
+    pb.flush(sch, 0);
+    if (ev_diag >= 0) {
+      sch.launches.push_back({Launch::EV_WAIT, 0, ev_diag, 0, 0, 0.0, 0, 1});
+      pb_rest.flush(sch, 1);
+      last_bulk_ev = sch.nevents++;
+      sch.launches.push_back({Launch::EV_RECORD, 0, last_bulk_ev, 0, 0, 0.0, 0, 1});
+    }
+  };
   // ---------------- forward:  L y = b  (levels deepest first).  X holds b and the running updates, the solved
   //                  blocks y land in X2 (out of place: Y = Winv * X per NBO-wide diagonal block).
   for (int d = S.nlevels - 1; d >= 0; d--) {
@@ -859,6 +886,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
       max_nob = std::max(max_nob, num_outer(S.sn_first[s + 1] - S.sn_first[s]));
     }
     for (int ph = 0; ph < 2 * max_nob + 1; ph++) {
+      bool updated = false;
       for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
         const int s = S.level_sn[q];
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
@@ -879,12 +907,21 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
           pb.add(make_op(Ys + (int64_t)b.o0 * R, 1, R, Xs + (int64_t)b.o0 * R, 1, R, b.winv, 1, b.ldw, nrhs, b.nbo,
                          b.nbo, 0));
         } else if (o1 < ns) {                      // x[o1:ns] -= L[o1:ns, o0:o1] y_b
+          // Look-ahead (wide fronts, many RHS): only the rows of the next diagonal block gate the chain; the rows
+          // beyond go to the bulk stream and overlap with the next diagonal steps (a few tiles each).
+          updated = true;
+          const int nx = std::min(ns, o1 + NBO);
+          const bool split = lookahead && (ns - nx) >= NBO;
           pb.add(make_op(Xs + (int64_t)o1 * R, 1, R, Ys + (int64_t)b.o0 * R, 1, R, P + o1 + (int64_t)b.o0 * ld, 1, ld,
-                         nrhs, ns - o1, b.nbo, GF_ACCUM | GF_NEG));
+                         nrhs, (split ? nx : ns) - o1, b.nbo, GF_ACCUM | GF_NEG));
+          if (split)
+            pb_rest.add(make_op(Xs + (int64_t)nx * R, 1, R, Ys + (int64_t)b.o0 * R, 1, R, P + nx + (int64_t)b.o0 * ld, 1, ld,
+                                nrhs, ns - nx, b.nbo, GF_ACCUM | GF_NEG));
         }
       }
-      pb.flush(pl->fwd);
+      flush_pair(pl->fwd, updated);
     }
+    if (last_bulk_ev >= 0) { pl->fwd.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0}); last_bulk_ev = -1; }
     add_pull_items(pl->fwd, S, vptr, d, 1, Launch::PULL_VEC, 4);
   }
   // ---------------- backward:  L' x = y  (roots first).  X2 holds y and the running updates, the solved blocks x
@@ -896,6 +933,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
       max_nob = std::max(max_nob, num_outer(S.sn_first[s + 1] - S.sn_first[s]));
     }
     for (int ph = 0; ph < 2 * max_nob + 1; ph++) {
+      bool updated = false;
       for (int q = S.level_ptr[d]; q < S.level_ptr[d + 1]; q++) {
         const int s = S.level_sn[q];
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
@@ -917,12 +955,20 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
           pb.add(make_op(Xs + (int64_t)b.o0 * R, 1, R, Ys + (int64_t)b.o0 * R, 1, R, b.winv, b.ldw, 1, nrhs, b.nbo,
                          b.nbo, 0));
         } else if (b.o0 > 0) {                     // y[0:o0] -= L[o0:o1, 0:o0]' x_b
-          pb.add(make_op(Ys, 1, R, Xs + (int64_t)b.o0 * R, 1, R, P + b.o0, ld, 1, nrhs, b.o0, b.nbo,
-                         GF_ACCUM | GF_NEG));
+          updated = true;
+          const int p0 = b.o0 - NBO;               // the block solved next is [p0, o0)
+          const bool split = lookahead && p0 >= NBO;
+          const int lo = split ? p0 : 0;
+          pb.add(make_op(Ys + (int64_t)lo * R, 1, R, Xs + (int64_t)b.o0 * R, 1, R, P + b.o0 + (int64_t)lo * ld, ld, 1, nrhs,
+                         b.o0 - lo, b.nbo, GF_ACCUM | GF_NEG));
+          if (split)
+            pb_rest.add(make_op(Ys, 1, R, Xs + (int64_t)b.o0 * R, 1, R, P + b.o0, ld, 1, nrhs, p0, b.nbo,
+                                GF_ACCUM | GF_NEG));
         }
       }
-      pb.flush(pl->bwd);
+      flush_pair(pl->bwd, updated);
     }
+    if (last_bulk_ev >= 0) { pl->bwd.launches.push_back({Launch::EV_WAIT, 0, last_bulk_ev, 0, 0, 0.0, 0, 0}); last_bulk_ev = -1; }
   }
   // ---------------- L * Z  (same dataflow as the forward sweep, products instead of solves)
   for (int d = S.nlevels - 1; d >= 0; d--) {

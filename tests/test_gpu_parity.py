@@ -335,6 +335,12 @@ def test_lookahead_streams_dense_front(slmm, eng, dense_first):
     Bm = rng.standard_normal((nd + nt, 7))
     assert rel_err(f(Bm), np.linalg.solve(V, Bm)) < 1e-10
     assert rel_err(L2 @ L2.T, V) < 1e-12
+    # many right-hand sides: the solve schedules use the same look-ahead (next diagonal block on the main stream,
+    # the rows beyond on the bulk stream); results must be reproducible bit for bit
+    Bw = rng.standard_normal((nd + nt, 96))
+    X1, X2 = f(Bw), f(Bw)
+    assert np.array_equal(X1, X2)
+    assert rel_err(X1, np.linalg.solve(V, Bw)) < 1e-10
 
 
 # ------------------------------------------------------------------------------------------ REML
