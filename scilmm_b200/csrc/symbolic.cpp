@@ -264,8 +264,18 @@ void column_counts(int n, const std::vector<int64_t>& bp, const std::vector<int3
 
 }  // namespace
 
-void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_perm, const SymbolicOptions& opt,
+void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_perm, const SymbolicOptions& opt_in,
              Symbolic& S) {
+  // relaxed-amalgamation overrides for experiments: SLMM_RELAX="n0,n1,n2,z0,z1,z2"
+  SymbolicOptions opt_local = opt_in;
+  if (const char* env = getenv("SLMM_RELAX")) {
+    double v[6];
+    if (sscanf(env, "%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6) {
+      for (int q = 0; q < 3; q++) { opt_local.nrelax[q] = (int)v[q]; opt_local.zrelax[q] = v[3 + q]; }
+    }
+  }
+  const SymbolicOptions& opt = opt_local;
+
   double t0 = now_s();
   S = Symbolic();
   S.n = n;
