@@ -27,7 +27,7 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 const std::string& last_error() { return g_last_error; }
 int64_t g_launch_count = 0;
 
-constexpr int NBO = 512;   // outer block: columns updated together with K = NBO
+constexpr int NBO = 1024;    // outer block: columns updated together with K = NBO
 
 // One pull work item: target columns (rows, for RHS blocks) [c0,c1) of parent front p, and the range [e0,e1) of
 // PullEntry records listing exactly the children that contribute to it (a parent can have > 1000 children, most

@@ -299,12 +299,12 @@ def test_extend_add_many_children_same_targets(slmm, eng, border):
 
 @pytest.mark.parametrize("dense_first", [False, True])
 def test_lookahead_streams_dense_front(slmm, eng, dense_first):
-    """A 2300-column dense front: outer blocks 0..4, so the trailing updates are split between the main and the bulk
+    """A 3300-column dense front: outer blocks 0..3 (1024 wide), so the trailing updates are split between the main and the bulk
     stream (look-ahead).  dense_first=True puts 300 coupled rows BELOW the wide supernode, so its Schur complement is
     built block by block on the third stream.  Factor twice and compare bit for bit (no races, fixed summation
     order), then check logdet / solve against LAPACK."""
     rng = np.random.default_rng(5)
-    nd, nt, nc = 2300, 400, 300 if dense_first else 60
+    nd, nt, nc = 3300, 400, 300 if dense_first else 60
     B = rng.standard_normal((nd, nd))
     D = B @ B.T / nd + 2.0 * np.eye(nd)
     T = sp.random(nt, nt, 0.02, random_state=1)
