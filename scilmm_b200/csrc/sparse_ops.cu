@@ -713,13 +713,9 @@ static uint64_t hash_bytes(const void* p, size_t nbytes) {
 }
 
 static int he_grid(int rows) {
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    const char* env = getenv("SLMM_HE_CTAS_PER_SM");     // experiment knob
-    per_sm = env ? std::max(1, atoi(env)) : 8;
-  }
+  // warp-per-row kernels with <= 64 registers (4 resident CTAs of 256 threads per SM): two waves over 148 SMs
   const int warps_needed = std::max(1, rows);
-  return std::max(1, std::min(148 * per_sm, (warps_needed + 7) / 8));
+  return std::max(1, std::min(148 * 8, (warps_needed + 7) / 8));
 }
 
 template <int G>
