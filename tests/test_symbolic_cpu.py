@@ -128,3 +128,24 @@ def test_library_exports_every_declared_symbol():
     assert declared <= exported, "missing: %s" % sorted(declared - exported)
     assert set(_lib.SIGNATURES) == declared
     assert _lib.lib().slmm_version() == 100
+
+
+def test_tuned_ordering_beats_metis_defaults(monkeypatch):
+    """The engine's METIS options (UFACTOR 10, NSEPS 3) must not cost more factorization flops than METIS' own
+    defaults on a pedigree pattern (guards the option indices against a different METIS build), and the experiment
+    overrides SLMM_METIS_OPT / SLMM_RELAX must be honoured."""
+    from scilmm_b200 import engine as E, pedigree as P
+    ped = P.simulate_pedigree(50000, 1e-3, seed=0, remove_frac=0.103125)     # large enough for ND to matter
+    A, T, D, F = P.numerator(ped["rel"])
+    keep, (A,) = P.drop_unrelated(A)
+    monkeypatch.delenv("SLMM_METIS_OPT", raising=False)
+    monkeypatch.delenv("SLMM_RELAX", raising=False)
+    tuned = E.SymbolicView(A, ordering="metis")
+    monkeypatch.setenv("SLMM_METIS_OPT", "16:200,15:1")           # METIS' defaults for node ND
+    stock = E.SymbolicView(A, ordering="metis")
+    assert tuned.flops <= stock.flops          # 5.8e9 against 6.5e9 here; 4.4e12 against 5.1e12 at the 250K config
+    assert tuned.flops != stock.flops                             # the override reached METIS
+    monkeypatch.delenv("SLMM_METIS_OPT")
+    monkeypatch.setenv("SLMM_RELAX", "0,0,0,0,0,0")               # no amalgamation: fundamental supernodes only
+    fund = E.SymbolicView(A, ordering="metis")
+    assert fund.nsuper > tuned.nsuper and fund.flops == tuned.flops and fund.lsize < tuned.lsize
