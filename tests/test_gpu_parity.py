@@ -428,3 +428,29 @@ def test_legacy_lmm_and_compute_he_vs_reference(golden_small, slmm):
     assert rel_err(out["covariates coefficients"], ref["lmm_beta"]) < 1e-6
     assert rel_err(out["covariance std"], ref["lmm_se"]) < 1e-5
     assert rel_err(out["covariates p-values"], ref["lmm_pvalues"]) < 1e-5
+
+
+def test_fused_assembly_bit_identical(golden_c1mini, slmm, eng):
+    """V assembled with one pass over two same-pattern matrices (slmm_chol_add_values2) equals, bit for bit, the
+    two-pass assembly and scipy's left-to-right matrices_weighted_sum (reference :55-59) scattered into the panels."""
+    g = golden_c1mini
+    mats = g.mats("k4")                       # A, A o A (same pattern), H, I
+    sig = g["sig_k4"]
+    chol = slmm.SparseCholesky(ordering_method="natural")
+    ses = chol._session(mats, g["cov"], g["y"] / g["y"].std())
+    assert ses.map_ids[0] == ses.map_ids[1]
+    e = ses.eng
+    e.add_values2(ses.map_ids[0], ses.matset.values_ptr(0), float(sig[0]), ses.matset.values_ptr(1), float(sig[1]), True)
+    for k in (2, 3):
+        e.add_values(ses.map_ids[k], ses.matset.values_ptr(k), float(sig[k]), False)
+    fused = e.panels().copy()
+    for k in range(4):
+        e.add_values(ses.map_ids[k], ses.matset.values_ptr(k), float(sig[k]), k == 0)
+    assert np.array_equal(fused, e.panels())
+    V = slmm.matrices_weighted_sum(mats, sig)
+    tgt = eng.SymbolicView(ses.union, ordering="natural").entry_map(sp.csr_matrix(V))
+    Vc = eng.canonical_csr(sp.csr_matrix(V))
+    ref = np.zeros_like(fused)
+    ok = tgt >= 0
+    ref[tgt[ok]] = Vc.data[ok]
+    assert np.array_equal(fused, ref)
