@@ -251,7 +251,7 @@ struct PhaseBuilder {
   void add(GemmOp op) {
     if (op.M <= 0 || op.N <= 0 || op.K <= 0) return;
     // Tile configuration: 128 x 128 tiles for large outputs; outputs that would leave most of the 148 SMs idle
-    // (the diagonal-block steps of the solves: nrhs x 512 with K = 512) take 64 x 64 tiles and, when K allows,
+    // (the diagonal-block steps of the solves: nrhs x NBO with K = NBO) take 64 x 64 tiles and, when K allows,
     // split K across CTAs into workspace partials that splitk_reduce_kernel adds in fixed order.
     const bool lower = op.flags & GF_LOWER;
     const int64_t tb = (int64_t)((op.M + 127) / 128) * ((op.N + 127) / 128);
@@ -792,7 +792,7 @@ static void build_factor_schedule(slmm_chol* h) {
   // ---- batched triangular inversion of the NBO-wide diagonal blocks of the NARROW fronts (64 < ns <= NBO; all
   //      supernodes at once, off every front's critical path; wide fronts built theirs above).  W = I, then forward
   //      substitution by NBI blocks:  W[t,:] = inv_t W[t,:];  W[t+1:,:] -= L[t+1:,t] W[t,:].  The multi-RHS solves
-  //      then need 2 GEMMs per 512 columns instead of per 64.
+  //      then need 2 GEMMs per NBO columns instead of per 64.
   if (!h->wblocks.empty()) {
     sch.launches.push_back({Launch::INIT_W, 0, (int32_t)h->wblocks.size(), (int32_t)h->wblocks.size(), 0, 0.0});
     for (int t = 0; t < NBO / NBI; t++) {
