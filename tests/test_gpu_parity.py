@@ -454,3 +454,41 @@ def test_fused_assembly_bit_identical(golden_c1mini, slmm, eng):
     ok = tgt >= 0
     ref[tgt[ok]] = Vc.data[ok]
     assert np.array_equal(fused, ref)
+
+
+def test_pedigree_scale_factor_vs_oracle_panels(slmm, eng):
+    """Scale guard (the extend-add race of round 1 only showed beyond ~50K individuals): simulated pedigree of 60K,
+    K = 3, nested-dissection ordering.  The factor must be bit-reproducible, agree panel by panel with the CPU
+    supernodal oracle on the same analysis, and solve V x = b to rounding."""
+    import bench
+    from oracle.supernodal_cpu import SupernodalCPUFactor, SupernodalPlan
+    from scilmm_b200 import pedigree as P
+    import torch
+    A, _, cov, y, info = bench.make_inputs(60000, 1e-3, 3)
+    n = A.shape[0]
+    mats = [A, P.epistasis(A), sp.eye(n).tocsr()]
+    sig = np.array([0.3, 0.15, 0.55])
+    chol = slmm.SparseCholesky(rng="device")
+    ses = chol._session(mats, cov, y / y.std())
+    ses.factor_at(sig)
+    L1, ld1 = ses.eng.panels(), ses.eng.logdet()
+    ses.factor_at(sig)
+    L2, ld2 = ses.eng.panels(), ses.eng.logdet()
+    assert ld1 == ld2 and np.array_equal(L1, L2)
+    V = (sig[0] * mats[0] + sig[1] * mats[1] + sig[2] * mats[2]).tocsr()
+    ref = SupernodalCPUFactor(V, plan=SupernodalPlan(ses.union, perm=ses.eng.perm()))
+    a = ref.plan.a
+    first, nrow, lptr = a['sn_first'], a['sn_nrow'], a['sn_lptr']
+    worst = 0.0
+    for s_ in range(len(nrow)):
+        ns, ms = first[s_ + 1] - first[s_], nrow[s_]
+        g = L2[lptr[s_]:lptr[s_] + ms * ns].reshape((ms, ns), order='F')
+        r = ref.Lx[lptr[s_]:lptr[s_] + ms * ns].reshape((ms, ns), order='F')
+        d = np.abs(g - r)
+        d[:ns][np.triu(np.ones((ns, ns), bool), 1)] = 0.0          # strict upper part of the diagonal block is unused
+        worst = max(worst, float(d.max()))
+    assert worst < 1e-10
+    assert abs(ld2 - ref.logdet()) < 1e-10 * abs(ref.logdet())
+    B = np.random.default_rng(3).standard_normal((n, 70))
+    X = ses.eng.solve_(eng.to_device(B)).cpu().numpy()
+    assert np.abs(V.dot(X) - B).max() < 1e-10 * np.abs(B).max()
