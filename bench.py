@@ -14,10 +14,18 @@ timed as a secondary result in the same line (`he`).
              (pinned) copied in, nll + gradient copied out, every step
   roofline   the dominant kernel (FP64 DMMA tile GEMM): issued dense flops / device time of its launches,
              measured with CUDA events on the launching stream in a separate profiled pass
-  cpu_baseline  the oracle port (oracle/estimation.py + oracle/supernodal_cpu.py) on the host cores
+  cpu_baseline  the oracle port (oracle/estimation.py + oracle/supernodal_cpu.py) on the host cores: a BOUNDED
+             sample (deterministic part in full, probe pipeline on --cpu-cols columns); the measured seconds and
+             the value scaled to all columns are reported as separate fields
 
 Multi-GPU (torchrun): factor replicated, probe columns sharded, one NCCL allreduce of K doubles per
-evaluation ("strong" scaling: total work fixed).  --impl reference runs the oracle CPU arm only.
+evaluation ("strong" scaling: total work fixed).
+
+--impl reference: the reference's algorithm on the host cores, nothing extrapolated - every step is one full
+`bolt_gradient_estimation` as oracle/estimation.py restates it (scipy sparse kernels, factor.L().dot(Z) and all 128
+probe columns), on the multifrontal LAPACK factor with the analysis repeated per evaluation as the reference does.
+A step takes ~1-2 minutes, so the arm runs one warm-up and then as many timed steps as fit in --ref-budget seconds
+(at least one) and prints the number it EXECUTED in "steps" (the request is kept in "steps_requested").
 """
 import argparse
 import json
@@ -95,8 +103,8 @@ def make_inputs(n, sf, ncov, seed=0, with_household=False):
     cov[:, :-1] -= cov[:, :-1].mean(axis=0)
     cov[:, :-1] /= cov[:, :-1].std(axis=0)
     y = y + cov[:, :-1].dot(np.full(ncov, 0.05))
-    info = dict(n_sim=n, n=nn, nnz=int(A.nnz), sf=sf, seed=seed, remove_frac=ped["remove_frac"],
-                gen_s=round(time.time() - t0, 1))
+    info = dict(n_sim=n, n=nn, nnz=int(A.nnz), sf=sf, seed=seed, remove_frac=ped["remove_frac"])
+    log("inputs generated in %.1f s" % (time.time() - t0), info)
     return A, (out[1] if with_household else None), cov, y, info
 
 
@@ -146,6 +154,17 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def gemm_traffic_record():
+    """DRAM traffic of the dominant kernel comes from an ncu --set full capture (never from a literal in this file):
+    profiles/gemm_traffic.json is written by scripts/ncu_summary.py from the .ncu-rep of one representative launch
+    and names the launch and the capture it came from.  Absent file -> traffic null."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+        return {"traffic": rec["dram_bytes"], "traffic_launch": rec["launch"], "traffic_source": rec["source"]}
+    except Exception:
+        return {"traffic": None, "traffic_source": "no ncu capture on file (profiles/gemm_traffic.json)"}
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -155,8 +174,9 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reml_sample(mats, cov, y, sig, reml, sim_num, sample_cols):
-    """Oracle REML evaluation on the host: full assembly + factorization + logdet + deterministic solves; the
-    probe pipeline (L*Z, solve, SpMM reductions) on `sample_cols` columns, scaled to sim_num columns."""
+    """BOUNDED sample of one oracle REML evaluation on the host: assembly, analysis, factorization, logdet and
+    the deterministic solves in full; the probe pipeline (L*Z, solve, SpMM reductions) on `sample_cols` of the
+    sim_num columns.  Returns the seconds actually measured and, separately, the value scaled to all columns."""
     from oracle import estimation as orc
     from oracle.supernodal_cpu import SupernodalCPUFactor, SupernodalPlan
     import scipy.linalg as la
@@ -190,9 +210,22 @@ def cpu_reml_sample(mats, cov, y, sig, reml, sim_num, sample_cols):
             _ = la.cho_solve(chol, ViC.T.dot(mats[k].dot(ViC)))
     t["quad"] = time.time() - t0
     scale = float(sim_num) / sample_cols
-    total_cached = t["assemble"] + t["factor"] + t["fixed"] + t["quad"] + scale * t["probe_sample"]
-    return dict(seconds=total_cached, seconds_with_reanalysis=total_cached + t["analyze"], parts=t, nll=nll,
-                logdet=logdet, flops=plan.sym.flops)
+    measured = sum(t.values())
+    scaled = measured + (scale - 1.0) * t["probe_sample"]
+    return dict(measured_s=measured, scaled_s=scaled, parts=t, nll=nll, logdet=logdet, flops=plan.sym.flops)
+
+
+def cpu_reml_full(mats, cov, y, sig, reml, sim_num, seed):
+    """One FULL oracle evaluation: oracle.estimation.reml_evaluation is the line-by-line restatement of the
+    reference's bolt_gradient_estimation (:77-117), here on the multifrontal LAPACK Factor with the analysis
+    repeated inside the call (reanalyze=True), scipy's single-threaded sparse kernels and factor.L().dot(Z)."""
+    from oracle import estimation as orc
+    from oracle.supernodal_cpu import supernodal_cholesky_func
+    np.random.seed(seed)
+    t0 = time.time()
+    nll, grad = orc.reml_evaluation(np.log(sig), supernodal_cholesky_func(reanalyze=True), mats, cov, y, reml,
+                                    sim_num, False, True)
+    return time.time() - t0, nll, grad
 
 
 def cpu_he(mats, cov, y):
@@ -218,6 +251,8 @@ def main():
     ap.add_argument("--skip-he", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-cols", type=int, default=8)
+    ap.add_argument("--ref-budget", type=float, default=300.0, help="seconds of timed steps in --impl reference")
+    ap.add_argument("--skip-fit", action="store_true", help="skip the full REML() fit (wall time incl. setup)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -227,6 +262,7 @@ def main():
     workload = "REML evaluation, simulated pedigree %d (sf=%g), K=3 (IBD, AoA, I), c=%d+1, %d probes" % (
         args.n, args.sf, args.ncov, args.probes)
 
+    base_config = {"workload": workload, "l2": "inputs larger than L2 (factor panels ~4.5 GB, matrices 1.5 GB)"}
     if args.impl == "reference":
         if rank != 0:
             return
@@ -235,25 +271,33 @@ def main():
         mats = [A, P.epistasis(A), sp.eye(A.shape[0]).tocsr()]
         ys = y / y.std()
         vals = []
-        for i in range(args.warmup + args.steps):
-            if i < args.warmup and i > 0:
-                continue                      # one warm-up pass is enough on the CPU (no clocks / caches to settle)
-            r = cpu_reml_sample(mats, cov, ys, sig, True, args.probes, args.cpu_cols)
-            log("reference step", i, r["parts"], "->", round(r["seconds_with_reanalysis"], 2), "s")
-            if i >= args.warmup:
-                vals.append(r["seconds_with_reanalysis"])
+        t_begin = time.time()
+        nwarm = min(1, args.warmup)          # one warm-up pass is enough on the CPU (no clocks / caches to settle)
+        i = 0
+        while True:
+            dt, nll_c, grad_c = cpu_reml_full(mats, cov, ys, sig, True, args.probes, seed=100 + i)
+            log("reference step %d: %.2f s  nll %.10e" % (i, dt, nll_c))
+            if i >= nwarm:
+                vals.append(dt)
+            i += 1
+            if len(vals) >= args.steps or (len(vals) >= 1 and sum(vals) + dt > args.ref_budget):
+                break
         v = float(np.mean(vals))
-        sample = ("oracle port: full assembly + METIS analysis + supernodal LAPACK factorization + logdet + "
-                  "deterministic solves; probe pipeline on %d of %d columns scaled x%g; analysis repeated per "
-                  "evaluation as the reference does" % (args.cpu_cols, args.probes, args.probes / args.cpu_cols))
+        sample = ("oracle port, nothing extrapolated: %d full evaluations (oracle.estimation.reml_evaluation = the "
+                  "reference's bolt_gradient_estimation line by line: scipy assembly, METIS analysis + multifrontal "
+                  "LAPACK factorization repeated per call, logdet, fixed-effect solves, factor.L().dot(Z) and the "
+                  "solve for all %d probe columns, scipy SpMM reductions) after %d warm-up; %d steps were requested, "
+                  "the time budget (--ref-budget %.0f s) allowed %d" % (len(vals), args.probes, nwarm, args.steps,
+                                                                         args.ref_budget, len(vals)))
         emit({"impl": "reference", "metric": "reml_iter_time", "value": v, "unit": "s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": workload, **info},
-                          "cpu_baseline": {"value": v, "unit": "s", "cores": os.cpu_count(), "kind": "port",
-                                           "sample": sample},
-                          "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+              "n_gpus": args.gpus, "steps": len(vals), "warmup": nwarm, "steps_requested": args.steps,
+              "warmup_requested": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
+              "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": {**base_config, **info},
+              "step_seconds": [round(x, 2) for x in vals], "wall_s": round(time.time() - t_begin, 1),
+              "cpu_baseline": {"value": v, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+              "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "nll": float(nll_c)})
         return
 
     import torch
@@ -286,14 +330,16 @@ def main():
     K = len(mats)
     s = args.probes
 
-    chol = S.SparseCholesky(rng="device")
+    E.UPLOAD_THREADS = max(1, min(4, (os.cpu_count() or 4) // max(1, world)))
+    chol = S.SparseCholesky(rng="device", seed=12345)     # counter-based device probes: same values for any N
     t0 = time.time()
     ses = chol._session(mats, cov, ys)
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     st = ses.eng.stats()
-    log("session %.1fs" % setup_s, {k: st[k] for k in ("nsuper", "nlevels", "nnzL", "lsize", "flops",
-                                                       "max_front_rows", "launches", "device_bytes")})
+    setup_parts = {k: round(v, 2) for k, v in ses.timings.items()}
+    log("session %.1fs" % setup_s, ses.timings, {k: st[k] for k in ("nsuper", "nlevels", "nnzL", "lsize", "flops",
+                                                                    "max_front_rows", "launches", "device_bytes")})
 
     # ---------------- device-resident steps
     sampler = ClockSampler(local_rank)
@@ -338,11 +384,27 @@ def main():
     t_asm = ev(assemble)
     t_fac = ev(assemble_factor) - t_asm
     Bs = torch.randn(n, s, dtype=torch.float64, device="cuda")
-    t_solve = ev(lambda: ses.eng.solve_(Bs.clone())) - ev(lambda: Bs.clone())
+    t_clone = ev(lambda: Bs.clone())
+    t_solve = ev(lambda: ses.eng.solve_(Bs.clone())) - t_clone
     t_lmul = ev(lambda: ses.eng.lmul(Bs))
+    Bn = torch.randn(n, cov.shape[1] + 1, dtype=torch.float64, device="cuda")
+    t_solve_narrow = ev(lambda: ses.eng.solve_(Bn.clone()))
     Xq = torch.randn(n, s + 1, dtype=torch.float64, device="cuda")
     groups = ses.matset.pattern_groups(2)
     t_quad = ev(lambda: [ses.matset.quadform_multi(ks, Xq) for ks in groups])
+    # the C3 "AI-REML iteration" of SURVEY 8d = one evaluation + compute_hess (reference :147-168)
+    t_hess = ev(lambda: S._hess_device(ses, ses.eng), reps=1)
+    # the phase that shards across ranks: this rank's probe columns through L*Z, the solve and the quadratic forms;
+    # and the same for ALL columns, which gives the Amdahl bound of the step at this N
+    lo_c, hi_c = S._shard.column_block(s, rank, world)
+    Bloc = Bs[:, lo_c:hi_c].contiguous()
+
+    def probe_pipeline(Bp):
+        W = ses.eng.solve_(ses.eng.lmul(Bp))
+        X = torch.cat([W, W[:, :1]], dim=1).contiguous()
+        return [ses.matset.quadform_multi(ks, X) for ks in groups]
+    t_shard_local = max_over_ranks(ev(lambda: probe_pipeline(Bloc)))
+    t_shard_full = ev(lambda: probe_pipeline(Bs)) if world > 1 else t_shard_local
     # profiled pass: per-kernel-kind device time with events around every launch
     assemble()
     ses.eng.set_profiling(True)
@@ -361,9 +423,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_tiles_kernel<128,128> (FP64 DMMA)", "achieved": round(achieved, 3),
                 "peak": round(dgemm_tflops, 3), "unit": "TFLOP/s", "frac": round(achieved / dgemm_tflops, 4),
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                # dram__bytes_read + write of ONE representative launch (ncu --set full): 16384 x 16384 lower-masked
-                # trailing update, K = 512 (4.6 ms, 2.06e11 flop) - profiles/r01_gemm_big_lower_K512_ncu.txt
-                "traffic": 1.7347e9, "traffic_launch": "M=N=16384 lower, K=512: 0.70 GB read + 1.03 GB written",
+                **gemm_traffic_record(),
                 "launches": gb["launches"], "kernel_ms_per_factorization": round(gb["ms"], 2),
                 "share_of_factorization": round(gb["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())), 3)}
     peaks = measured_peaks()
@@ -376,9 +436,19 @@ def main():
     half = [(z + n) / 2.0 for z in nnzs]
     quad_bytes = 12.0 * half[0] + 4 * (n + 1) + 8.0 * half[1] + 12.0 * half[2] + 4 * (n + 1) + 2 * 8.0 * n * (s + 1)
     quad_gather_bytes = (half[0] + half[2]) * 8.0 * (s + 1)
+    solve_flops = 4.0 * st["nnzL"] * s
     phases = {
         "assemble_ms": round(t_asm, 3), "factorize_ms": round(t_fac, 2), "solve128_ms": round(t_solve, 2),
         "lmul128_ms": round(t_lmul, 2), "quadforms_ms": round(t_quad, 2),
+        "solve_narrow_ms": round(t_solve_narrow, 2), "solve_narrow_cols": int(cov.shape[1] + 1),
+        "solve_narrow_gbs": round((2.0 * 8.0 * st["lsize"]) / t_solve_narrow / 1e6, 1),
+        "solve128_tflops": round(solve_flops / t_solve / 1e9, 2),
+        "compute_hess_ms": round(t_hess, 2), "ai_reml_iter_ms": round(step_ms + t_hess, 2),
+        "sharded_phase_ms": round(t_shard_local, 2), "sharded_phase_all_columns_ms": round(t_shard_full, 2),
+        # Amdahl bound of the step at this N: the replicated assembly + factorization + 1/N of the probe pipeline
+        # (the fixed-effect solve runs beside the pipeline on the auxiliary stream)
+        "replicated_ms": round(t_asm + t_fac, 2),
+        "amdahl_bound_ms": round(t_asm + t_fac + t_shard_full / world, 2),
         "cholesky_gflops": round(st["flops"] / t_fac / 1e6, 1),
         "cholesky_issued_gflops": round(st["issued_flops"] / t_fac / 1e6, 1),
         "solve_gbs": round(solve_bytes / t_solve / 1e6, 1), "quadforms_gbs": round(quad_bytes / t_quad / 1e6, 1),
@@ -418,14 +488,41 @@ def main():
         nll_h, grad_h = S.bolt_gradient_estimation(log_sig, chol_h, mats, cov, ys, True, s, False)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    e2e = {"value": round(e2e_s, 4), "unit": "s", "h2d_bytes_per_step": int(Zhost.numel() * 8 + K * 8),
+    lo_e, hi_e = S._shard.column_block(s, rank, world)
+    e2e = {"value": round(e2e_s, 4), "unit": "s", "h2d_bytes_per_step": int(n * (hi_e - lo_e) * 8 + K * 8),
            "d2h_bytes_per_step": int((K + 1) * 8 + (K * (cov.shape[1] ** 2 + 2) + 2 * cov.shape[1] ** 2) * 8),
            "api": "scilmm_b200.bolt_gradient_estimation(log_sig, SparseCholesky(), mats, cov, y, True, 128, False)"}
+
+    # ---------------- a whole REML() fit through the public API, setup included (fresh functor: upload, analysis,
+    # scatter maps, HE start, L-BFGS-B evaluations, final factorization, fixed effects, compute_hess)
+    full_fit = None
+    if not args.skip_fit:
+        del ses
+        chol._sessions.clear()
+        chol._engines.clear()
+        chol_h._sessions.clear()
+        chol_h._engines.clear()
+        release_host_caches(torch)
+        chol_f = S.SparseCholesky(rng="device", seed=777)
+        barrier()
+        t0 = time.perf_counter()
+        fit = S.REML(chol_f, mats[:-1], cov, y, reml=True, sim_num=s, verbose=False)
+        torch.cuda.synchronize()
+        fit_s = max_over_ranks(time.perf_counter() - t0)
+        ses_f = next(iter(chol_f._sessions.values()))
+        full_fit = {"wall_s": round(fit_s, 2), "setup_s": round(ses_f.setup_s, 2),
+                    "setup_parts_s": {k: round(v, 2) for k, v in ses_f.timings.items()},
+                    "evaluations": int(ses_f.n_eval), "sigma2": [float(v) for v in fit["covariance coefficients"]],
+                    "se": [float(v) for v in fit["covariance std"]], "nll": float(fit["nll"]),
+                    "api": "scilmm_b200.REML(SparseCholesky(rng='device'), [A, AoA], cov, y, sim_num=128)"}
+        log("full fit", full_fit)
+        del ses_f, chol_f, fit
+        ses = None
 
     # ---------------- HE (config 4) secondary result
     he = None
     log("before HE:", host_mem())
-    del ses, chol, chol_h, Zhost, Bs, Xq, Bchk, Xchk, VX
+    del ses, chol, chol_h, Zhost, Bs, Bn, Bloc, Xq, Bchk, Xchk, VX
     release_host_caches(torch)
     if not args.skip_he:
         try:
@@ -441,29 +538,34 @@ def main():
         if abs(r["nll"] - nll_h) > 1e-10 * abs(r["nll"]) or abs(r["logdet"] - parity["logdet"]) > 1e-10 * abs(r["logdet"]):
             raise RuntimeError("GPU result differs from the CPU oracle beyond 1e-10: nll %r vs %r, logdet %r vs %r"
                                % (nll_h, r["nll"], parity["logdet"], r["logdet"]))
-        cpu = {"value": round(r["seconds_with_reanalysis"], 2), "unit": "s", "cores": os.cpu_count(), "kind": "port",
-               "value_analysis_cached": round(r["seconds"], 2),
+        cpu = {"value": round(r["scaled_s"], 2), "unit": "s", "cores": os.cpu_count(), "kind": "port",
+               "measured_s": round(r["measured_s"], 2),
+               "value_note": "value = measured_s with the probe-pipeline part scaled from %d to %d columns; the "
+                             "--impl reference arm runs every column and extrapolates nothing" % (args.cpu_cols, s),
                "parts_s": {k: round(v, 2) for k, v in r["parts"].items()},
                "cholesky_gflops": round(r["flops"] / r["parts"]["factor"] / 1e9, 1),
                "nll_rel_diff_vs_gpu": abs(r["nll"] - nll_h) / abs(r["nll"]),
                "logdet_rel_diff_vs_gpu": abs(r["logdet"] - parity["logdet"]) / abs(r["logdet"]),
                "sample": "oracle port (CHOLMOD is not installed): full assembly, METIS analysis, supernodal LAPACK "
-                         "factorization on all cores, logdet, deterministic solves; probe pipeline on %d of %d "
-                         "columns scaled x%g; value includes the per-evaluation re-analysis the reference performs"
-                         % (args.cpu_cols, s, s / args.cpu_cols)}
+                         "factorization on all cores, logdet, deterministic solves; probe pipeline (BLAS L*Z, solve, "
+                         "scipy SpMM reductions) on %d of %d columns; includes the per-evaluation re-analysis the "
+                         "reference performs" % (args.cpu_cols, s)}
 
     if rank == 0:
         out = {"metric": "reml_iter_time", "value": round(step_ms / 1e3, 5), "unit": "s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 3),
                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": workload, "l2": "inputs larger than L2 (factor panels %.1f GB)" %
-                          (st["lsize"] * 8 / 1e9), **info, "nnzL": st["nnzL"], "factor_flops": st["flops"],
-                          "nsuper": st["nsuper"], "levels": st["nlevels"], "max_front": st["max_front_rows"],
-                          "symbolic_s": round(st["t_order"] + st["t_symbolic"], 2), "session_setup_s": round(setup_s, 1),
-                          "parallelism": "probe columns sharded x%d, factor replicated" % world},
+               "config": {**base_config, **info},
+               "stats": {"nnzL": st["nnzL"], "factor_flops": st["flops"], "panel_gb": round(st["lsize"] * 8 / 1e9, 2),
+                         "nsuper": st["nsuper"], "levels": st["nlevels"], "max_front": st["max_front_rows"],
+                         "symbolic_s": round(st["t_order"] + st["t_symbolic"], 2), "session_setup_s": round(setup_s, 1),
+                         "session_setup_parts_s": setup_parts, "device_bytes": st["device_bytes"],
+                         "parallelism": "probe columns sharded x%d, factor replicated" % world,
+                         "probe_stream": "device Philox4x32-10 keyed by (seed, evaluation, row, column): identical "
+                                         "values for any number of GPUs"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-               "phases": phases, "parity": parity, "cpu_baseline": cpu, "he": he,
+               "phases": phases, "parity": parity, "cpu_baseline": cpu, "full_fit": full_fit, "he": he,
                "nll": float(nll), "grad": [float(g) for g in grad]}
         emit(out)
     if world > 1:
@@ -471,20 +573,22 @@ def main():
 
 
 def bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks):
-    """Haseman-Elston fit, K=3 (IBD, AoA, household), BASELINE config 4; row blocks sharded across ranks."""
+    """Haseman-Elston fit, K=3 (IBD, AoA, household), BASELINE config 4.  With N ranks every rank uploads and holds
+    only its row block of every matrix (blocks balanced by the entries on/below the diagonal)."""
     from scilmm_b200 import sharding
     rank, world = sharding.rank_world()
     A, H, cov, y, info = make_inputs(args.he_n, args.he_sf, 2, seed=0, with_household=True)
     n = A.shape[0]
     mats = [A, P.epistasis(A), H]
     log("HE inputs", info, "nnz(H)", H.nnz, "|", host_mem())
-    ms = E.MatSet(mats)
-    yd = E.to_device(y)
-    bounds = sharding.row_blocks_by_nnz(A.indptr, world)
+    bounds = sharding.row_blocks_by_lower_nnz(A, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    ms = E.MatSet(mats, row_range=(lo, hi))
+    ms.resolve_symmetry_sharded(sharding.allreduce_sum_)
+    yd = E.to_device(y)
 
     def run():
-        part = ms.he_moments_device(yd, lo, hi)
+        part = ms.he_moments_device(yd)
         return sharding.allreduce_sum_(part)
 
     for _ in range(3):
@@ -499,6 +603,11 @@ def bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks):
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
     alg_bytes = (12.0 * A.nnz + 4 * (n + 1)) + 8.0 * A.nnz + (12.0 * H.nnz + 4 * (n + 1)) + 3 * 8.0 * n
+    # bytes the symmetric half traversal really has to move (entries on/below the diagonal): the honest denominator
+    half = lambda z: (z + n) / 2.0
+    real_bytes = (12.0 * half(A.nnz) + 8.0 * half(A.nnz) + 12.0 * half(H.nnz)) + 3 * 4 * (n + 1) + 3 * 8.0 * n
+    h2d_local = int(ms.h2d_bytes + 8 * n)
+    del ms
     e2e_s = 1e30
     for _ in range(2):          # best of two public calls (host page-locking / allocator noise on a shared box)
         barrier()
@@ -508,13 +617,17 @@ def bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks):
         e2e_s = min(e2e_s, max_over_ranks(time.perf_counter() - t0))
     out = {"workload": "HE fit, simulated pedigree %d (sf=%g), K=3 (IBD, AoA, household)" % (args.he_n, args.he_sf),
            **info, "nnz_household": int(H.nnz), "n_gpus": world, "device_ms": round(dev_ms, 4),
-           "e2e_s": round(e2e_s, 3), "h2d_bytes": int(ms.h2d_bytes + 8 * n), "estimates": [float(v) for v in est],
+           "e2e_s": round(e2e_s, 3), "h2d_bytes_per_rank": h2d_local, "rows_this_rank": [lo, hi],
+           "estimates": [float(v) for v in est],
            "roofline": {"bound": "hbm", "kernel": "he_group_kernel<2> (IBD + AoA, lower triangle) + he_short_kernel (household) + "
                                   "he_cross_mapped_kernel<1,2> + reduce_all_kernel",
                         "bytes_formula": "SURVEY 8d: sum_k 12 nnz_k + 4(n+1) per pattern (8 nnz for a matrix sharing a "
-                                         "pattern) + 3*8n; the symmetric traversal reads about half of it from DRAM",
+                                         "pattern) + 3*8n; frac_real_bytes counts only the entries on/below the "
+                                         "diagonal, which is what the symmetric traversal moves",
                         "achieved": round(alg_bytes / dev_ms / 1e6, 1), "peak": hbm * world, "unit": "GB/s",
-                        "frac": round(alg_bytes / dev_ms / 1e6 / (hbm * world), 4), "algorithmic_bytes": alg_bytes}}
+                        "frac": round(alg_bytes / dev_ms / 1e6 / (hbm * world), 4), "algorithmic_bytes": alg_bytes,
+                        "achieved_real_bytes": round(real_bytes / dev_ms / 1e6, 1),
+                        "frac_real_bytes": round(real_bytes / dev_ms / 1e6 / (hbm * world), 4)}}
     if not args.skip_cpu and rank == 0 and world == 1:
         t_cpu, est_cpu = cpu_he(mats, cov, y)
         out["cpu_baseline"] = {"value": round(t_cpu, 2), "unit": "s", "cores": 1, "kind": "port",

@@ -50,6 +50,19 @@ int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* h_indptr, co
 /* borrow device-resident CSR arrays for matrix k (same_as >= 0: pattern identical to matrix same_as) */
 int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indptr, const int32_t* d_indices,
                             const double* d_data, int64_t nnz, int32_t same_as);
+/* Row-block shard of the HE path (SparseCholesky.py:215-232 moments): the set holds only rows
+ * [row_begin, row_end) of every matrix.  Call before binding; the arrays then bound are the rows' slices (indptr of
+ * row_end - row_begin + 1 entries starting at 0, indices / data of the block, columns global).  Such a set serves
+ * slmm_he_moments only. */
+int slmm_matset_set_row_range(slmm_matset_t* ms, int32_t row_begin, int32_t row_end);
+/* Symmetry of a sharded matrix: h_out2[0] / h_out2[1] = order-independent 64-bit hash sums of the stored entries
+ * above / below the diagonal under the key (min, max, value bits).  Sum both over all shards (wrapping add): the
+ * matrix equals its transpose iff the two totals agree; then tell every shard with slmm_matset_set_symmetric. */
+int slmm_matset_symmetry_hash(slmm_matset_t* ms, int32_t k, uint64_t* h_out2);
+int slmm_matset_set_symmetric(slmm_matset_t* ms, int32_t k, int32_t flag);
+/* Pageable host array -> device through a ring of persistent pinned buffers filled by `threads` worker threads
+ * (0 = default 4); ordered with the default stream on both sides.  The e2e upload of the scipy CSR arrays. */
+int slmm_upload_h2d(void* d_dst, const void* h_src, int64_t nbytes, int32_t threads);
 int slmm_matset_nnz(const slmm_matset_t* ms, int32_t k, int64_t* out);
 int slmm_matset_values(const slmm_matset_t* ms, int32_t k, const double** d_data_out);
 
@@ -98,6 +111,15 @@ int slmm_device_arrays_equal_i32(const int32_t* d_a, const int32_t* d_b, int64_t
 /* *out = 1 when A_k equals its transpose bit for bit (device check, cached). */
 int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out);
 int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);
+/* *out = 1 when the n x n CSR matrix in device memory equals its transpose bit for bit (pattern and values).
+ * Guards the factor input: the engine keeps one triangle after the fill-reducing permutation, which is only
+ * CHOLMOD's answer (it reads the lower triangle, SparseCholesky.py:23-26) when both triangles agree. */
+int slmm_device_csr_is_symmetric(const int32_t* d_indptr, const int32_t* d_indices, const double* d_data, int32_t n,
+                                 int32_t* out);
+/* *out = 1 when every entry of pattern A is present in pattern B (sorted rows, device arrays): lets the host pick
+ * the union pattern of V = sum_k sigma_k A_k (matrices_weighted_sum, SparseCholesky.py:55-59) without sparse adds. */
+int slmm_device_pattern_subset(const int32_t* d_indptr_a, const int32_t* d_indices_a, const int32_t* d_indptr_b,
+                               const int32_t* d_indices_b, int32_t n, int32_t* out);
 
 /* ------------------------------------------------------------------ sparse Cholesky ------------------- */
 /* Symbolic analysis of a symmetric pattern given as CSR/CSC with both triangles (host arrays).  Replaces the
@@ -117,6 +139,17 @@ int slmm_chol_perm(const slmm_chol_t* h, int32_t* h_perm);
 /* Register the pattern of one input matrix (any CSR/CSC subset of the analysed pattern, host arrays) and get a
  * scatter map id; values with that pattern can then be streamed into the factor storage. */
 int slmm_chol_register_pattern(slmm_chol_t* h, const int32_t* h_indptr, const int32_t* h_indices, int32_t* map_id);
+/* Same with an explicit triangle rule.  tri == 0: both triangles are stored with identical values (the caller has
+ * verified it, e.g. slmm_device_csr_is_symmetric).  tri != 0: CHOLMOD's rule - sksparse.cholmod.cholesky reads only
+ * the lower triangle of the CSC matrix it is given (SparseCholesky.py:23-26): tri > 0 keeps the entries with
+ * index >= row of the given arrays (lower triangle of CSC arrays), tri < 0 those with index <= row (lower triangle
+ * of CSR arrays); the other triangle is ignored. */
+int slmm_chol_register_pattern_tri(slmm_chol_t* h, const int32_t* h_indptr, const int32_t* h_indices, int32_t tri,
+                                   int32_t* map_id);
+/* Same from device-resident CSR arrays (e.g. those of a slmm_matset_t): the scatter map is built by a kernel, no
+ * host pass over the entries and no 8-byte-per-entry upload. */
+int slmm_chol_register_pattern_device(slmm_chol_t* h, const int32_t* d_indptr, const int32_t* d_indices, int64_t nnz,
+                                      int32_t tri, int32_t* map_id);
 /* V assembly (matrices_weighted_sum, SparseCholesky.py:55-59), fused with the scatter into the permuted
  * supernodal panels:  panels = 0 ; panels += sigma * values  for each call, in call order (rounded multiply then
  * rounded add, the order scipy uses).  first != 0 clears the panels before adding. */
@@ -135,6 +168,11 @@ int slmm_chol_logdet(slmm_chol_t* h, double* h_out);
 int slmm_chol_solve(slmm_chol_t* h, double* d_B, int32_t nrhs, int32_t mode);
 /* (factor.L().dot(Z))[argsort(P)]  (SparseCholesky.py:50-51): d_out in original ordering, C-ordered n x nrhs */
 int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrhs);
+/* Z = np.random.randn(n, sim_num) of simulate_vector (SparseCholesky.py:50) drawn on the device: columns
+ * [col_begin, col_begin + ncols) of the n x sim_num block of evaluation `stream`, written C-ordered n x ncols.
+ * Counter-based (Philox4x32-10, Box-Muller): the value of (row, global column) depends only on (seed, stream), never
+ * on how the columns are split over GPUs.  Distribution-equivalent to, not stream-identical with, numpy's MT19937. */
+int slmm_probe_normals(double* d_out, int64_t n, int32_t ncols, int32_t col_begin, uint64_t seed, uint64_t stream);
 /* factor.L() as host CSC (colptr int64[n+1], rowidx int32[nnz], values double[nnz]; nnz = stats i[5]) */
 int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, double* h_values);
 
@@ -147,7 +185,8 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* h_colptr, int32_t* h_rowidx, dou
  * factorization) instead of stream 0, so that a narrow solve (the c+1 fixed-effect columns, SparseCholesky.py:30,32)
  * - a launch-latency-bound chain that leaves the SMs idle - overlaps the probe pipeline (:50-52) the caller issues
  * on stream 0 next.  slmm_chol_aux_join makes stream 0 wait for the auxiliary work; the solved block must not be
- * read (or freed) before it.  The two solves must use different RHS widths (plans are per width). */
+ * read (or freed) before it.  Solve plans (work buffers, launch graphs) are kept per (RHS width, section), so the
+ * two solves may have the same width. */
 int slmm_chol_aux_begin(slmm_chol_t* h);
 int slmm_chol_aux_end(slmm_chol_t* h);
 int slmm_chol_aux_join(slmm_chol_t* h);
@@ -175,6 +214,8 @@ int slmm_symbolic_arrays(const slmm_symbolic_t* s, int32_t* perm, int32_t* paren
 /* scatter map of a registered pattern into the panel storage (what slmm_chol_register_pattern uploads) */
 int slmm_symbolic_entry_map(const slmm_symbolic_t* s, const int32_t* h_indptr, const int32_t* h_indices,
                             int64_t* h_target);
+int slmm_symbolic_entry_map_tri(const slmm_symbolic_t* s, const int32_t* h_indptr, const int32_t* h_indices,
+                                int32_t tri, int64_t* h_target);
 
 /* FP64 DMMA self-test / microbenchmark of the tile GEMM (C = A B^T, column-major); returns elapsed ms */
 int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,

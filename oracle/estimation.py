@@ -240,6 +240,55 @@ def he_regression(mat_list, cov, y, MQS=False, verbose=False, sim_num=100, compu
     return est, np.sqrt(np.diag(var))
 
 
+def minque(cholesky_func, mat_list, cov, y, compute_stderr=False, verbose=False, num_iter=100, sim_num=100,
+           normal_source=None):
+    """Iterated MINQUE. reference: SparseCholesky.py:284-347.
+
+    First pass (H = I, :296) is the MQS moments; later passes weight by H^-1 with Monte-Carlo traces through
+    probes of covariance H (:303-306).  Reproduces the stale loop index in the update of H (:335: every matrix
+    after the first is weighted by minque_est[K-1]).  compute_stderr returns (est, 0.0) as the reference (:343-347).
+    """
+    CtC = cov.T.dot(cov)
+    y = y - cov.dot(np.linalg.solve(CtC, cov.T.dot(y)))
+    y /= y.std()
+    K = len(mat_list)
+    n = y.shape[0]
+    H = None
+    for it in range(num_iter):
+        q = np.zeros(K)
+        S = np.zeros((K, K))
+        if H is not None:
+            factor = cholesky_func(H)
+            Z = np.random.randn(n, sim_num) if normal_source is None else normal_source(n, sim_num)
+            sim_y = factor.L().dot(Z)[np.argsort(factor.P())]
+            Hi_sim = factor(sim_y)
+            Hi_y = factor(y)
+        for i in range(K):
+            if H is None:
+                q[i] = y.dot(mat_list[i].dot(y)) - y.dot(y)
+            else:
+                q[i] = Hi_y.dot(mat_list[i].dot(Hi_y)) - y.dot(y)
+                Hi_Ki_Hi_sim = factor(mat_list[i].dot(Hi_sim))
+            for j in range(i + 1):
+                if H is None:
+                    S[i, j] = (mat_list[i].multiply(mat_list[j])).sum() - (n - 1)
+                else:
+                    S[i, j] = np.mean(np.einsum('ij,ij->j', Hi_sim, mat_list[j].dot(Hi_Ki_Hi_sim))) - (n - 1)
+                S[j, i] = S[i, j]
+        est = np.linalg.solve(S, q)
+        if verbose:
+            print(it + 1, est)
+        stale_i = K - 1
+        H = mat_list[0] * est[0]
+        for m in mat_list[1:]:
+            H = H + m * est[stale_i]
+        H = H + sp.eye(n, format='csr') * (1.0 - est.sum())
+    est = np.linalg.solve(S, q)
+    if not compute_stderr:
+        return est
+    return est, np.sqrt(0)
+
+
 # ----------------------------------------------------------------------------- legacy entry points
 def legacy_lmm(cholesky_func, mats, C, y, with_intercept=True, reml=True, sim_num=100, verbose=False):
     """reference: scilmm/Estimation/LMM.py:154-171 (LMM) with compute_sigmas :111-124 (equal starting components,

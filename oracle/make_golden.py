@@ -147,14 +147,28 @@ def build_case(SC, ped, num, phe, n_sim, sf, seed, c, sim_num):
         g["reml_sig_%s" % tag] = out["covariance coefficients"]
         g["reml_beta_%s" % tag] = out["covariates coefficients"]
         g["reml_se_%s" % tag] = out["covariance std"]
+
+    # ---- MINQUE (reference :284-347), 2 iterations (one factorization of H; a third makes H indefinite on these inputs) under a frozen stream, identity permutation
+    import contextlib
+    import io
+    for tag, mats in (("k1", [A]), ("k3", [A, epi, hh])):
+        np.random.seed(seed + 6)
+        with contextlib.redirect_stdout(io.StringIO()):          # the reference prints every iteration (:330)
+            g["minque_%s" % tag] = SC.MINQUE(chol, list(mats), cov, y.copy(), num_iter=2, sim_num=sim_num)
     return g
 
 
 def main():
     SC, ped, num, phe = load_reference()
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    # case_c1 is BASELINE.json config 1 at its stated size: simulate_tree(10000, 1e-3, 1.4, 0.8) -> ~7.1K individuals
+    # after the no-relatives filter, 1 IBD matrix (+ the K=4 variants), 2 covariates + intercept, sim_num 100
     for name, kw in (("case_small", dict(n_sim=400, sf=0.01, seed=11, c=2, sim_num=20)),
-                     ("case_c1mini", dict(n_sim=2500, sf=0.004, seed=0, c=2, sim_num=100))):
+                     ("case_c1mini", dict(n_sim=2500, sf=0.004, seed=0, c=2, sim_num=100)),
+                     ("case_c1", dict(n_sim=10000, sf=0.001, seed=0, c=2, sim_num=100))):
+        if only and name not in only:
+            continue
         g = build_case(SC, ped, num, phe, **kw)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **g)

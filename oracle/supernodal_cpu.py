@@ -89,8 +89,11 @@ class SupernodalPlan(object):
 
 
 class SupernodalCPUFactor(object):
+    """plan: a SupernodalPlan (symbolic borrowed from the engine: same ordering and supernodes, panel-by-panel
+    comparable) or an oracle.symbolic_ref.IndependentPlan (symbolic computed without the product library)."""
+
     def __init__(self, V, plan=None, ordering="metis", perm=None):
-        from scilmm_b200.engine import canonical_csr
+        from oracle.symbolic_ref import _csr32 as canonical_csr
         Vc = sp.csr_matrix((V.data, V.indices, V.indptr), shape=V.shape) if sp.isspmatrix_csc(V) else V
         Vc = canonical_csr(Vc)
         if plan is None:

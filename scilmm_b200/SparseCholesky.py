@@ -34,6 +34,18 @@ def _pattern_key(m):
     return (m.shape[0], int(m.nnz), h.hexdigest())
 
 
+def _fingerprint(a, max_samples=1 << 12, with_sum=False):
+    """Cheap content fingerprint of a host array: shape + a hash of <= max_samples evenly strided elements
+    (+ the full sum for the small dense inputs).  It is what makes the session cache notice in-place edits
+    (`A.data *= 2`, a permuted phenotype) without hashing 10^8 values on every likelihood evaluation; an edit that
+    touches none of the sampled elements and keeps the sum needs SparseCholesky.invalidate()."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    step = max(1, flat.size // max_samples)
+    h = hashlib.blake2b(np.ascontiguousarray(flat[::step]).view(np.uint8), digest_size=8).hexdigest()
+    return (a.shape, h, float(flat.sum()) if with_sum else 0.0)
+
+
 class B200Factor(object):
     """The Factor protocol of sksparse.cholmod (the four members the reference uses)."""
 
@@ -91,24 +103,26 @@ class SparseCholesky(object):
          'host_buffer' takes them from `probe_source(n, sim_num)` (a host array / pinned tensor).
     """
 
-    def __init__(self, use_long=False, mode='supernodal', ordering_method='nesdis', perm=None, rng='numpy'):
+    def __init__(self, use_long=False, mode='supernodal', ordering_method='nesdis', perm=None, rng='numpy', seed=0):
         self._use_long = use_long
         self._mode = mode
         self._ordering_method = ordering_method
         self._perm = perm
         self.rng = rng
+        self.seed = int(seed)         # key of the counter-based device probe stream (rng == 'device')
         self.probe_source = None      # callable(n, sim_num) -> host block, used when rng == 'host_buffer'
         self._engines = {}
         self._sessions = {}
         self.timings = {}
 
-    def _engine_for(self, pattern):
-        key = _pattern_key(pattern)
+    def _engine_for(self, pattern, key=None):
+        key = key or _pattern_key(pattern)
         eng = self._engines.get(key)
         if eng is None:
             t0 = time.time()
             eng = _eng.CholEngine(pattern, ordering=self._ordering_method, perm=self._perm)
-            eng._self_map = eng.register_pattern(pattern)
+            eng._self_map = None
+            eng._dev_pattern = None
             self.timings['analyze_s'] = time.time() - t0
             if len(self._engines) >= 4:
                 self._engines.pop(next(iter(self._engines)))
@@ -116,27 +130,49 @@ class SparseCholesky(object):
         return eng
 
     def __call__(self, sparse_mat):
+        """Factor V.  Like sksparse.cholmod.cholesky (reference :23-26) only the LOWER triangle of the CSC matrix
+        defines V: an input whose two triangles differ (or that stores one triangle only) is symmetrised from its
+        lower triangle first (device check per call; symmetric input - the reference's case - takes no extra
+        pass)."""
         torch = _eng.require_cuda()
         if not sparse.issparse(sparse_mat):
             raise TypeError("SparseCholesky expects a scipy.sparse matrix")
         m = sparse_mat
-        if not sparse.isspmatrix_csc(m) and not sparse.isspmatrix_csr(m):
+        if not sparse.isspmatrix_csc(m):
             m = m.tocsc()
         if m.shape[0] != m.shape[1]:
             raise ValueError("matrix must be square")
         if not m.has_sorted_indices:
             m = m.sorted_indices()
-        pat = sparse.csr_matrix((m.data, m.indices, m.indptr), shape=m.shape)   # symmetric: CSC == CSR
-        pat = _eng.canonical_csr(pat)
-        eng = self._engine_for(pat)
+        pat = _eng.canonical_csr(sparse.csr_matrix((m.data, m.indices, m.indptr), shape=m.shape))   # = V' as CSR
+        key = _pattern_key(pat)
+        eng = self._engines.get(key)
         vals = _eng.to_device(pat.data, torch)
+        dev = eng._dev_pattern if eng is not None and eng._dev_pattern is not None else \
+            (_eng.to_device(pat.indptr, torch), _eng.to_device(pat.indices, torch))
+        if not _eng.device_csr_is_symmetric(dev[0], dev[1], vals, pat.shape[0]):
+            low = sparse.tril(m, format='csc')
+            full = (low + sparse.tril(low, -1, format='csc').T).tocsc()
+            full.sort_indices()
+            return self.__call__(full)
+        if eng is None:
+            eng = self._engine_for(pat, key)
+        if eng._dev_pattern is None:
+            eng._dev_pattern = dev
+            eng._self_map = eng.register_pattern_device(dev[0], dev[1], pat.nnz, 0)
         eng.add_values(eng._self_map, vals.data_ptr(), 1.0, True)
         eng.factorize()
         return B200Factor(eng)
 
+    def invalidate(self):
+        """Forget the cached REML sessions (device copies of mats / covariates / y).  The cache notices in-place
+        edits through a sampled content fingerprint; call this after an edit it could miss."""
+        self._sessions.clear()
+
     # ---- fused session for the REML objective: matrices resident, patterns registered once
     def _session(self, mats, covariates, y):
-        key = (tuple(id(m) for m in mats), id(covariates), id(y))
+        key = (tuple((id(m), int(m.nnz), _fingerprint(m.data)) for m in mats),
+               (id(covariates), _fingerprint(covariates, with_sum=True)), (id(y), _fingerprint(y, with_sum=True)))
         ses = self._sessions.get(key)
         if ses is None:
             self._sessions.clear()
@@ -154,30 +190,56 @@ class RemlSession(object):
         self.functor = functor
         self._refs = (list(mats), covariates, y)     # keeps the ids used as the cache key alive
         self.mats_host = [_eng.canonical_csr(m) for m in mats]
-        self.K = len(mats)
+        self.K = K = len(mats)
         self.n = self.mats_host[0].shape[0]
         t0 = time.time()
-        union = None
-        for m in self.mats_host:        # pattern union (values are irrelevant; ones avoid cancellation)
-            ones = sparse.csr_matrix((np.ones(m.nnz), m.indices, m.indptr), shape=m.shape)
-            union = ones if union is None else union + ones
-        union = _eng.canonical_csr(union)
-        self.union = union
-        self.eng = functor._engine_for(union)
+        self.timings = {}
+        # matrices go to HBM first: pattern sharing, CSR sanity, symmetry and the union pattern are all decided by
+        # kernels on the resident arrays - the host never adds or scans the 10^8-entry patterns
         self.matset = _eng.MatSet(self.mats_host)
+        self._groups = self.matset.pattern_groups(2)
+        self._sym = [self.matset.is_symmetric(k) for k in range(K)]
+        self.timings['upload_s'] = time.time() - t0
+        t1 = time.time()
+        leaders = sorted(set(self.matset.pattern_id(k) for k in range(K)))
+        big = max(leaders, key=lambda k: self.matset.nnz[k])
+        if all(self.matset.pattern_is_subset(k, big) for k in leaders):
+            union = self.mats_host[big]                 # every pattern is contained in the largest one
+        else:
+            union = None
+            for k in leaders:       # pattern union (values are irrelevant; ones avoid cancellation)
+                m = self.mats_host[k]
+                ones = sparse.csr_matrix((np.ones(m.nnz), m.indices, m.indptr), shape=m.shape)
+                union = ones if union is None else union + ones
+            union = _eng.canonical_csr(union)
+        if not all(self._sym):
+            # V is defined by the lower triangles (CHOLMOD reads only the lower triangle of the CSC sum, reference
+            # :23-26 after :59); the analysis needs the structurally symmetric pattern
+            ones = sparse.csr_matrix((np.ones(union.nnz), union.indices, union.indptr), shape=union.shape)
+            union = _eng.canonical_csr(ones + ones.T)
+        self.union = union
+        self.timings['union_s'] = time.time() - t1
+        t1 = time.time()
+        self.eng = functor._engine_for(union)
+        self.timings['analyze_s'] = time.time() - t1
+        t1 = time.time()
         self.map_ids = []
         cache = {}
-        for m in self.mats_host:
-            k = _pattern_key(m)
-            if k not in cache:
-                cache[k] = self.eng.register_pattern(m)
-            self.map_ids.append(cache[k])
+        for k in range(K):
+            tri = 0 if self._sym[k] else -1
+            ck = (self.matset.pattern_id(k), tri)
+            if ck not in cache:
+                ptr_t, idx_t, _ = self.matset.device_arrays(k)
+                cache[ck] = self.eng.register_pattern_device(ptr_t, idx_t, self.matset.nnz[k], tri)
+            self.map_ids.append(cache[ck])
+        self.timings['maps_s'] = time.time() - t1
         self.C = _eng.to_device(np.asarray(covariates, dtype=np.float64), torch)
         self.y = _eng.to_device(np.asarray(y, dtype=np.float64), torch)
         self.C_host = np.asarray(covariates, dtype=np.float64)
         self.y_host = np.asarray(y, dtype=np.float64)
         self.setup_s = time.time() - t0
-        self._groups = None
+        self.n_eval = 0               # evaluations so far: the `stream` index of the device probe generator
+        self.overlap = True           # fixed-effect solve on the auxiliary stream beside the probe pipeline
         self.last = {}
 
     # K1 + K2
@@ -229,21 +291,30 @@ class RemlSession(object):
         return ViC, chol, beta, Viy
 
     def probes(self, sim_num, Z=None, col_begin=0, col_end=None):
-        """W = V^-1 (L Z)[argsort P]   (reference :49-52)."""
+        """W = V^-1 (L Z)[argsort P]   (reference :49-52) for the probe columns [col_begin, col_end) of the
+        n x sim_num block Z.  rng == 'device' draws ONLY those columns, from the counter-based stream keyed by
+        (functor.seed, evaluation index, row, global column): the same values for any number of GPUs."""
         torch = self.torch
+        col_end = sim_num if col_end is None else col_end
         if Z is None:
-            if self.functor.rng == 'numpy':
-                Z = _eng.to_device(np.random.randn(self.n, sim_num), torch)
+            if self.functor.rng == 'numpy':               # the reference's global stream: the whole block is drawn
+                Z = np.random.randn(self.n, sim_num)
             elif self.functor.rng == 'host_buffer':       # caller-supplied host block (pinned tensor or ndarray)
                 Z = self.functor.probe_source(self.n, sim_num)
             else:
-                Z = torch.randn(self.n, sim_num, dtype=torch.float64, device="cuda")
+                Z = self.eng.probe_normals(self.n, col_end - col_begin, col_begin, self.functor.seed, self.n_eval)
+                col_begin, col_end = 0, Z.shape[1]
         if not torch.is_tensor(Z):
-            Z = _eng.to_device(np.asarray(Z, dtype=np.float64), torch)
-        elif not Z.is_cuda:
-            Z = Z.to("cuda", non_blocking=True)
-        if col_end is not None or col_begin:
-            Z = Z[:, col_begin:col_end].contiguous()
+            Z = np.asarray(Z, dtype=np.float64)
+            if col_begin or col_end != Z.shape[1]:        # slice on the host: only the local columns are uploaded
+                Z = np.ascontiguousarray(Z[:, col_begin:col_end])
+            Z = _eng.to_device(Z, torch)
+        else:
+            if col_begin or col_end != Z.shape[1]:
+                Z = Z[:, col_begin:col_end]
+            if not Z.is_cuda:
+                Z = Z.contiguous().to("cuda", non_blocking=True)
+            Z = Z.contiguous()
         U = self.eng.lmul(Z)
         return self.eng.solve_(U)
 
@@ -253,13 +324,12 @@ class RemlSession(object):
         self.factor_at(sigmas)
         logdet = self.eng.logdet()
         n = self.n
-        pending = self._fixed_effects_start()          # narrow solve on the auxiliary stream ...
+        pending = self._fixed_effects_start(self.overlap)   # narrow solve on the auxiliary stream ...
         # ... beside the probe pipeline; probe columns are sharded across ranks when torch.distributed is initialised
         rank, world = _shard.rank_world()
-        if Z is None and self.functor.rng == 'numpy' and world > 1:
-            Z = np.random.randn(n, sim_num)            # every rank draws the same stream, keeps its slice
         lo, hi = _shard.column_block(sim_num, rank, world)
-        W = self.probes(sim_num, Z, lo, hi) if world > 1 else self.probes(sim_num, Z)
+        W = self.probes(sim_num, Z, lo, hi)
+        self.n_eval += 1
         ViC, chol, beta, Viy = self._fixed_effects_finish(pending)
         beta_t = torch.from_numpy(beta).to("cuda")
         Vir = Viy - ViC @ beta_t                       # V^-1 (y - C beta) by linearity
@@ -277,9 +347,6 @@ class RemlSession(object):
         # B = [V^-1 C | V^-1 r]: its last diagonal entry is r'V^-1 A_k V^-1 r (:66), its leading c x c block feeds
         # the REML trace term (:70).
         s_loc = W.shape[1]
-        if self._groups is None:
-            self._groups = self.matset.pattern_groups(2)
-            self._sym = [self.matset.is_symmetric(k) for k in range(K)]
         Bq = self._ViCy
         Bq[:, c] = Vir                                 # Viy was copied out above; the block becomes [V^-1 C | V^-1 r]
         for ks in self._groups:
@@ -408,30 +475,38 @@ def estimate_var_comps(cholesky_func, mats, covariates, y, reml=True, sim_num=10
     return np.exp(optObj.x)
 
 
-def _hess_device(ses, factor_eng):
-    """-0.5 y' P A_i P A_j P y on the device (reference :147-168)."""
+def _hess_device(ses, factor_eng, pre=None):
+    """-0.5 y' P A_i P A_j P y on the device (reference :147-168) in THREE multi-RHS solves instead of the
+    reference's 1 + K + K(K+1)/2 single-column ones: [C | y] (c+1 columns; reused from the caller when `pre` =
+    (ViC, chol, Viy) is given), the K columns A_j P y, and the K(K+1)/2 columns A_i P A_j P y."""
     torch = ses.torch
     K = ses.K
     C, y = ses.C, ses.y
-    ViC = factor_eng.solve_(C.clone().contiguous())
-    chol = la.cho_factor((C.t() @ ViC).cpu().numpy())
-    Minv = torch.from_numpy(la.cho_solve(chol, np.eye(C.shape[1]))).to("cuda")
+    c = C.shape[1]
+    if pre is None:
+        B = torch.cat([C, y.unsqueeze(1)], dim=1).contiguous()
+        factor_eng.solve_(B)
+        ViC, Viy = B[:, :c].contiguous(), B[:, c].contiguous()
+        chol = la.cho_factor((C.t() @ ViC).cpu().numpy())
+    else:
+        ViC, chol, Viy = pre
+    Minv = torch.from_numpy(la.cho_solve(chol, np.eye(c))).to("cuda")
 
-    def project(Zb):          # Zb: n x k block
-        Viz = factor_eng.solve_(Zb.clone().contiguous())
+    def project_solved(Viz):  # Viz = V^-1 z  ->  P z
         return Viz - ViC @ (Minv @ (C.t() @ Viz))
 
-    Py = project(y.unsqueeze(1))
+    def project(Zb):          # Zb: n x k block
+        return project_solved(factor_eng.solve_(Zb.clone().contiguous()))
+
+    Py = project_solved(Viy.unsqueeze(1))
     AjPy = torch.cat([ses.matset.spmm(j, Py) for j in range(K)], dim=1)       # n x K
     PAjPy = project(AjPy)
+    pairs = [(i, j) for j in range(K) for i in range(j + 1)]
+    cols = torch.cat([ses.matset.spmm(i, PAjPy[:, j:j + 1].contiguous()) for (i, j) in pairs], dim=1)
+    vals = (-0.5 * (y @ project(cols))).cpu().numpy()
     hess = np.empty((K, K))
-    for j in range(K):
-        cols = torch.cat([ses.matset.spmm(i, PAjPy[:, j:j + 1].contiguous()) for i in range(j + 1)], dim=1)
-        Pcols = project(cols)
-        vals = (-0.5 * (y @ Pcols)).cpu().numpy()
-        for i in range(j + 1):
-            hess[i, j] = vals[i]
-            hess[j, i] = vals[i]
+    for q, (i, j) in enumerate(pairs):
+        hess[i, j] = hess[j, i] = vals[q]
     return hess
 
 
@@ -478,7 +553,7 @@ def REML(cholesky_func, mats, covariates, y, reml=True, sim_num=100, verbose=Fal
     nll = 0.5 * (float(r @ Vir) + y.size * LOG_2PI + factor.logdet())
     if reml:
         nll += 0.5 * 2 * np.sum(np.log(np.diag(chol[0])))
-    hess = _hess_device(ses, ses.eng)
+    hess = _hess_device(ses, ses.eng, pre=(ViC, chol, Viy))
     sigmas_sigmas = np.sqrt(np.diag(la.inv(-hess)) * (1 + 1.0 / sim_num))
     return {"covariance coefficients": varcomp_estimates,
             "covariates coefficients": fixed_effects,
@@ -489,18 +564,33 @@ def REML(cholesky_func, mats, covariates, y, reml=True, sim_num=100, verbose=Fal
 
 # ------------------------------------------------------------------------------------------- Haseman-Elston
 def he_moments(mat_list, y, MQS=False, matset=None):
-    """q and S of the HE normal equations on the GPU (reference :213-243)."""
-    ms = matset if matset is not None else _eng.MatSet(mat_list)
+    """q and S of the HE normal equations on the GPU (reference :213-243).
+
+    With torch.distributed initialised (world > 1) the rows are sharded: every rank uploads and holds ONLY its row
+    block of every matrix (blocks balanced by the entries on/below the diagonal, which is what the kernels read),
+    computes its partial moments, and one all-reduce of 2K + 2K^2 doubles combines them."""
     torch = _eng.require_cuda()
+    rank, world = _shard.rank_world()
+    if matset is not None:
+        ms = matset
+    elif world == 1:
+        ms = _eng.MatSet(mat_list)
+    else:
+        big = max(range(len(mat_list)), key=lambda k: mat_list[k].nnz)
+        bounds = _shard.row_blocks_by_lower_nnz(sparse.csr_matrix(mat_list[big]), world)
+        ms = _eng.MatSet(mat_list, row_range=(int(bounds[rank]), int(bounds[rank + 1])))
     K, n = ms.K, ms.n
     y_dev = _eng.to_device(np.asarray(y, dtype=np.float64), torch)
-    rank, world = _shard.rank_world()
-    if world == 1:
+    if ms.row_range == (0, n) and world == 1:
         out = ms.he_moments_device(y_dev).cpu().numpy()
-    else:       # row blocks balanced by nonzeros + one all-reduce of 2K + 2K^2 doubles
+    elif ms.row_range == (0, n):      # whole matrices on every rank (caller-supplied set): shard the rows only
         big = max(range(K), key=lambda k: ms.nnz[k])
         bounds = _shard.row_blocks_by_nnz(_eng._csr_arrays(mat_list[big])[0], world)
         part = ms.he_moments_device(y_dev, int(bounds[rank]), int(bounds[rank + 1])).clone()
+        out = _shard.allreduce_sum_(part).cpu().numpy()
+    else:
+        ms.resolve_symmetry_sharded(_shard.allreduce_sum_)
+        part = ms.he_moments_device(y_dev).clone()
         out = _shard.allreduce_sum_(part).cpu().numpy()
     q_off, q_diag, S_off, S_diag = _eng.MatSet.split_moments(out, K)
     if MQS:
@@ -512,11 +602,19 @@ def he_moments(mat_list, y, MQS=False, matset=None):
     return q, S, ms
 
 
-def HE(mat_list, cov, y, MQS=False, verbose=False, sim_num=100, compute_stderr=False, y2=None):
+def HE(mat_list, cov, y, MQS=False, verbose=False, sim_num=100, compute_stderr=False, y2=None, fix_indices=False):
     """Haseman-Elston regression, reference :192-281 (same outputs, including the bivariate mode's in-place
-    mutation of mat_list / y2 and the reference's K>1 indexing quirks in the sampling-variance branch)."""
-    if any(not sparse.issparse(m) for m in mat_list):
-        raise TypeError("scilmm_b200.HE takes scipy.sparse matrices (the dense branch of the reference is CPU-only)")
+    mutation of mat_list / y2).
+
+    Dense (ndarray) matrices - the reference's `else` branches at :224-231 - are converted to CSR and take the same
+    kernels (explicit zeros contribute nothing to any moment).  sim_num=None is the reference's exact sampling
+    variance (:260-268): <H A_i - H, H A_j - H>_F accumulated over blocks of unit vectors with SpMM kernels instead of
+    sparse x sparse products (O(n/128) passes: small problems only, like the reference's).
+
+    fix_indices=False reproduces the reference's K>1 indexing slips in the sampling-variance branch bit for bit
+    (:254 weights every matrix after the first by he_est[K-1]; :262 rebinds mat_i to mat_list[j]; :267,:272 read the
+    stale mat_j = mat_list[K-1]); they are harmless for K = 1.  fix_indices=True evaluates what the code intends:
+    H = sum_k he_k A_k + (1 - sum he) I and V_q[i,j] = 2 tr(H (A_i - I) H (A_j - I))."""
     CTC = cov.T.dot(cov)
     y = y - cov.dot(np.linalg.solve(CTC, cov.T.dot(y)))
     y /= y.std()
@@ -525,22 +623,22 @@ def HE(mat_list, cov, y, MQS=False, verbose=False, sim_num=100, compute_stderr=F
         y2 /= y2.std()
         y = np.concatenate((y, y2))
         for m_i, m in enumerate(mat_list):
+            m = m if sparse.issparse(m) else sparse.csr_matrix(np.asarray(m, dtype=np.float64))
             z = sparse.csr_matrix((m.shape[0], m.shape[0]))
             mat_list[m_i] = sparse.vstack([sparse.hstack([z, m]), sparse.hstack([m, z])]).tocsr()
-    K = len(mat_list)
+    mats = [m if sparse.issparse(m) else sparse.csr_matrix(np.asarray(m, dtype=np.float64)) for m in mat_list]
+    K = len(mats)
     n = y.shape[0]
-    q, S, ms = he_moments(mat_list, y, MQS)
+    q, S, ms = he_moments(mats, y, MQS)
     he_est = np.linalg.solve(S, q)
     if not compute_stderr:
         return he_est
 
     torch = _eng.require_cuda()
-    stale_i = K - 1            # reference :254 reads the loop variable left over from :216
-    stale_j = K - 1            # reference :272 reads mat_j left over from :224
-    w = np.zeros(K)
-    w[0] += he_est[0]
-    for k in range(1, K):
-        w[k] += he_est[stale_i]
+    if ms.row_range != (0, ms.n):
+        ms = _eng.MatSet(mats)          # the sampling-variance products need whole matrices on every rank
+    stale = K - 1                       # reference :254 / :267,:272: loop variables left over from :216-232
+    w = np.array([he_est[k if (fix_indices or k == 0) else stale] for k in range(K)])
     w_eye = 1.0 - he_est.sum()
 
     def Hdot(X):
@@ -550,18 +648,34 @@ def HE(mat_list, cov, y, MQS=False, verbose=False, sim_num=100, compute_stderr=F
                 out = out + w[k] * ms.spmm(k, X)
         return out
 
+    def minus_identity(k, X):           # (A_k - I) X
+        return ms.spmm(k, X) - X
+
     V_q = np.empty((K, K))
-    if sim_num is None:
-        raise NotImplementedError("the exact (sim_num=None) branch forms sparse x sparse products (reference "
-                                  ":261,267) and has no GPU kernel; use sim_num")
     for i in range(K):
         for j in range(i + 1):
-            Zs = _eng.to_device(np.random.randn(n, sim_num), torch)
-            t1 = ms.spmm(stale_j, Zs) - Zs
-            t2 = Hdot(t1)
-            t3 = ms.spmm(j, t2) - t2          # the inner loop rebinds mat_i to mat_list[j] (:262)
-            t4 = Hdot(t3)
-            V_q[i, j] = 2 * float((Zs * t4).sum(dim=0).mean())
+            if fix_indices:
+                right, left = j, i
+            else:
+                right, left = stale, j  # the inner loop rebinds mat_i to mat_list[j] (:262); mat_j is stale
+            if sim_num is None:
+                # exact branch (:260-268): 2 <H A_i - H, H A_j - H>_F, column block by column block
+                a_idx = i
+                b_idx = i if j == i else (j if fix_indices else stale)
+                acc = torch.zeros((), dtype=torch.float64, device="cuda")
+                for c0 in range(0, n, 128):
+                    c1 = min(n, c0 + 128)
+                    E = torch.zeros(n, c1 - c0, dtype=torch.float64, device="cuda")
+                    E[torch.arange(c0, c1, device="cuda"), torch.arange(c1 - c0, device="cuda")] = 1.0
+                    Ua = Hdot(minus_identity(a_idx, E))
+                    Ub = Ua if b_idx == a_idx else Hdot(minus_identity(b_idx, E))
+                    acc += (Ua * Ub).sum()
+                V_q[i, j] = 2 * float(acc)
+            else:
+                Zs = _eng.to_device(np.random.randn(n, sim_num), torch)
+                t2 = Hdot(minus_identity(right, Zs))
+                t4 = Hdot(minus_identity(left, t2))
+                V_q[i, j] = 2 * float((Zs * t4).sum(dim=0).mean())
             V_q[j, i] = V_q[i, j]
     var_he_est = np.linalg.solve(S, np.linalg.solve(S, V_q).T).T
     return he_est, np.sqrt(np.diag(var_he_est))

@@ -36,6 +36,10 @@ SIGNATURES = {
     "slmm_matset_destroy": (C.c_int, [vp]),
     "slmm_matset_upload": (C.c_int, [vp, i32, vp, vp, vp]),
     "slmm_matset_bind_device": (C.c_int, [vp, i32, vp, vp, vp, i64, i32]),
+    "slmm_matset_set_row_range": (C.c_int, [vp, i32, i32]),
+    "slmm_matset_symmetry_hash": (C.c_int, [vp, i32, vp]),
+    "slmm_matset_set_symmetric": (C.c_int, [vp, i32, i32]),
+    "slmm_upload_h2d": (C.c_int, [vp, vp, i64, i32]),
     "slmm_matset_nnz": (C.c_int, [vp, i32, C.POINTER(i64)]),
     "slmm_matset_values": (C.c_int, [vp, i32, pp]),
     "slmm_he_moments": (C.c_int, [vp, vp, i32, i32, vp]),
@@ -54,12 +58,18 @@ SIGNATURES = {
     "slmm_chol_stats": (C.c_int, [vp, vp, vp]),
     "slmm_chol_perm": (C.c_int, [vp, vp]),
     "slmm_chol_register_pattern": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
+    "slmm_chol_register_pattern_tri": (C.c_int, [vp, vp, vp, i32, C.POINTER(i32)]),
+    "slmm_chol_register_pattern_device": (C.c_int, [vp, vp, vp, i64, i32, C.POINTER(i32)]),
+    "slmm_device_csr_is_symmetric": (C.c_int, [vp, vp, vp, i32, C.POINTER(i32)]),
+    "slmm_device_pattern_subset": (C.c_int, [vp, vp, vp, vp, i32, C.POINTER(i32)]),
+    "slmm_symbolic_entry_map_tri": (C.c_int, [vp, vp, vp, i32, vp]),
     "slmm_chol_add_values": (C.c_int, [vp, i32, vp, f64, i32]),
     "slmm_chol_add_values2": (C.c_int, [vp, i32, vp, f64, vp, f64, i32]),
     "slmm_chol_factorize": (C.c_int, [vp, C.POINTER(i32)]),
     "slmm_chol_logdet": (C.c_int, [vp, C.POINTER(f64)]),
     "slmm_chol_solve": (C.c_int, [vp, vp, i32, i32]),
     "slmm_chol_lmul": (C.c_int, [vp, vp, vp, i32]),
+    "slmm_probe_normals": (C.c_int, [vp, i64, i32, i32, C.c_uint64, C.c_uint64]),
     "slmm_chol_export_L": (C.c_int, [vp, vp, vp, vp]),
     "slmm_chol_copy_panels": (C.c_int, [vp, vp]),
     "slmm_chol_aux_begin": (C.c_int, [vp]),

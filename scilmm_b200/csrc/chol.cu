@@ -149,6 +149,75 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, double* __res
   }
 }
 
+// Scatter map of one input pattern into the panel storage, built ON THE DEVICE from the device-resident CSR arrays
+// (the host version walks 10^8 entries with a binary search each and then uploads 8 bytes per entry).  Warp per row.
+// tri: see symbolic.cpp entry_map.  *bad is set when an entry falls outside the analysed pattern.
+__global__ void __launch_bounds__(256) entry_map_kernel(const int32_t* __restrict__ ap, const int32_t* __restrict__ ai,
+                                                        int n, const int32_t* __restrict__ iperm,
+                                                        const int32_t* __restrict__ col2sn, DevSym S, int tri,
+                                                        int64_t* __restrict__ target, int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const int pr = iperm[r];
+    const int b = ap[r], e = ap[r + 1];
+    for (int p = b + lane; p < e; p += 32) {
+      const int c = ai[p];
+      const int pc = iperm[c];
+      int ir = pr, ic = pc;
+      int64_t out = -1;
+      bool take = true;
+      if (tri == 0) take = ic <= ir;
+      else {
+        take = !((tri > 0 && c < r) || (tri < 0 && c > r));
+        if (ic > ir) { ir = pc; ic = pr; }
+      }
+      if (take) {
+        const int s = col2sn[ic];
+        const int ms = S.sn_nrow[s];
+        const int32_t* rows = S.rows + S.sn_rowptr[s];
+        const int pos = lower_bound_dev(rows, ms, ir);
+        if (pos < ms && rows[pos] == ir) out = S.sn_lptr[s] + (int64_t)(ic - S.sn_first[s]) * ms + pos;
+        else *bad = 1;
+      }
+      target[p] = out;
+    }
+  }
+}
+
+// Hutchinson probe block Z ~ N(0,1) (np.random.randn(n, sim_num), reference scilmm/SparseCholesky.py:50) drawn on
+// the device from a COUNTER-BASED stream: element (row i, global column c) of evaluation `stream` is a pure function
+// of (seed, stream, i, c) - Philox4x32-10 keyed by the seed, counter (i, c, stream) - so a rank that owns columns
+// [col_begin, col_begin + ncols) draws exactly the values the single-GPU run draws for them: results do not depend
+// on the number of GPUs, and only the local columns are ever generated.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256) probe_normals_kernel(double* __restrict__ out, int64_t n, int ncols, int col_begin,
+                                                            uint64_t seed, uint64_t stream) {
+  const int64_t total = n * ncols;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / ncols;
+    const int c = (int)(q - i * ncols) + col_begin;
+    uint32_t x[4];
+    philox4x32_10((uint32_t)i, (uint32_t)c, (uint32_t)stream, (uint32_t)(stream >> 32) ^ (uint32_t)(i >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    const uint64_t a = (((uint64_t)x[0] << 32) | x[1]) >> 11, b = (((uint64_t)x[2] << 32) | x[3]) >> 11;
+    const double u1 = ((double)a + 0.5) * 0x1.0p-53, u2 = ((double)b + 0.5) * 0x1.0p-53;    // both in (0, 1)
+    out[q] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);                                       // Box-Muller
+  }
+}
+
 struct WBlock { int64_t off; int32_t n, pad; };
 
 // identity into every wide (outer-block) inverse slot, before the batched triangular inversion
@@ -213,6 +282,10 @@ struct Schedule {
   PotrfOp* d_potrf = nullptr;
   PullItem* d_pull = nullptr;
   double flops = 0;
+  // CUDA graphs of this launch list (built lazily on first use; every kernel argument is fixed per schedule):
+  // [0] the look-ahead variant on the priority + bulk stream pair, [1] the serial variant (one stream)
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  bool graph_failed = false;
   void upload() {
     if (ws_size > 0) {              // patch workspace offsets into pointers
       d_ws = dev_alloc<double>(ws_size);
@@ -228,6 +301,7 @@ struct Schedule {
     d_pull_entries = dev_upload(pull_entries.data(), pull_entries.size());
   }
   void release() {
+    for (int q = 0; q < 2; q++) if (gexec[q]) { cudaGraphExecDestroy(gexec[q]); gexec[q] = nullptr; }
     dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_reduce); dev_free(d_tile_op); dev_free(d_pull_entries);
     d_tile_op = nullptr; d_pull_entries = nullptr;
     d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr; d_ws = nullptr; d_reduce = nullptr;
@@ -380,7 +454,7 @@ struct slmm_chol {
   Symbolic S;
   // device copies of the symbolic structure
   int32_t *d_sn_first = nullptr, *d_sn_nrow = nullptr, *d_rows = nullptr, *d_rel = nullptr, *d_child_ptr = nullptr,
-          *d_child_idx = nullptr, *d_col2sn = nullptr, *d_perm = nullptr;
+          *d_child_idx = nullptr, *d_col2sn = nullptr, *d_perm = nullptr, *d_iperm = nullptr;
   int64_t *d_sn_rowptr = nullptr, *d_sn_lptr = nullptr, *d_sn_uptr = nullptr;
   std::vector<int64_t> uptr, invptr;
   std::vector<int64_t> wptr;          // [nsuper+1] offsets of the wide inverse blocks of each supernode
@@ -474,48 +548,115 @@ static bool is_kernel(const Launch& L) { return L.kind != Launch::EV_RECORD && L
 // updates on a second one, ordered by events; both are forked from / joined to the default stream, so callers see
 // plain stream-0 semantics.  The list order is a valid topological order: the profiling mode simply runs it
 // serially on one stream with an event pair around every kernel.
-static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena, const int64_t* d_vptr,
-                         int nrhs) {
+//
+// The lists are static (every kernel argument is fixed once the schedule is uploaded), so each one is captured
+// ONCE into a CUDA graph and replayed: a 12-column solve is a chain of ~1000 tiny launches whose cost was the
+// host's launch rate, not the kernels (SLMM_GRAPHS=0 falls back to launch-by-launch).
+static void issue_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena,
+                           const int64_t* d_vptr, int nrhs, bool two, cudaStream_t one) {
   const DevSym ds = h->devsym();
+  for (const Launch& L : sch.launches) {
+    cudaStream_t st = two ? (L.stream ? h->s_bulk : h->s_main) : one;
+    if (L.kind == Launch::EV_RECORD) { if (two) CUDA_OK(cudaEventRecord(h->events[L.count], st)); continue; }
+    if (L.kind == Launch::EV_WAIT) { if (two) CUDA_OK(cudaStreamWaitEvent(st, h->events[L.count], 0)); continue; }
+    launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs, st);
+  }
+}
+
+static bool graphs_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SLMM_GRAPHS"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+// Captures the launch list into a graph.  Capture happens on the (non-blocking) priority stream - the legacy
+// default stream cannot be captured; the bulk stream joins the capture through the fork event.
+static cudaGraphExec_t capture_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena,
+                                        const int64_t* d_vptr, int nrhs, bool two) {
+  cudaStream_t origin = h->s_main;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CUDA_OK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed));
+  try {
+    if (two) {
+      CUDA_OK(cudaEventRecord(h->ev_fork, origin));
+      CUDA_OK(cudaStreamWaitEvent(h->s_bulk, h->ev_fork, 0));
+    }
+    issue_schedule(h, sch, X, vec_arena, d_vptr, nrhs, two, origin);
+    if (two) {
+      CUDA_OK(cudaEventRecord(h->ev_join, h->s_bulk));
+      CUDA_OK(cudaStreamWaitEvent(origin, h->ev_join, 0));
+    }
+    CUDA_OK(cudaGetLastError());
+  } catch (...) {
+    cudaStreamEndCapture(origin, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    throw;
+  }
+  CUDA_OK(cudaStreamEndCapture(origin, &graph));
+  const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  CUDA_OK(e);
+  return exec;
+}
+
+static void run_schedule(slmm_chol* h, Schedule& sch, double* X, double* const* vec_arena, const int64_t* d_vptr,
+                         int nrhs) {
   int64_t nk = 0;
+  for (const Launch& L : sch.launches) nk += is_kernel(L) ? 1 : 0;
+  if (nk == 0) return;
   if (!h->profiling) {
     // schedules with events run on the priority + bulk stream pair; inside an auxiliary section (cur != 0) the
     // pair may already be in use by the solve on stream 0, so the list is walked serially (a valid order)
     const bool two = sch.nevents > 0 && h->s_main != nullptr && h->cur == nullptr;
-    if (two) {
-      while ((int)h->events.size() < sch.nevents) {
-        cudaEvent_t e;
-        CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->events.push_back(e);
+    while ((int)h->events.size() < sch.nevents) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->events.push_back(e);
+    }
+    const int gi = two ? 0 : 1;
+    if (graphs_enabled() && h->s_main != nullptr && !sch.graph_failed && sch.gexec[gi] == nullptr) {
+      try {
+        sch.gexec[gi] = capture_schedule(h, sch, X, vec_arena, d_vptr, nrhs, two);
+      } catch (const std::exception&) {
+        sch.graph_failed = true;      // fall back to launch-by-launch for this schedule
+        sch.gexec[gi] = nullptr;
       }
+    }
+    cudaGraphExec_t exec = (graphs_enabled() && !sch.graph_failed) ? sch.gexec[gi] : nullptr;
+    if (exec != nullptr && h->cur != nullptr) {
+      CUDA_OK(cudaGraphLaunch(exec, h->cur));              // auxiliary section: the whole list on the auxiliary stream
+    } else if (exec != nullptr || two) {
+      // fork from / join to the legacy default stream around the priority stream (and, inside, the bulk stream)
       CUDA_OK(cudaEventRecord(h->ev_fork, 0));
       CUDA_OK(cudaStreamWaitEvent(h->s_main, h->ev_fork, 0));
-      CUDA_OK(cudaStreamWaitEvent(h->s_bulk, h->ev_fork, 0));
-    }
-    for (const Launch& L : sch.launches) {
-      cudaStream_t st = two ? (L.stream ? h->s_bulk : h->s_main) : h->cur;
-      if (L.kind == Launch::EV_RECORD) { if (two) CUDA_OK(cudaEventRecord(h->events[L.count], st)); continue; }
-      if (L.kind == Launch::EV_WAIT) { if (two) CUDA_OK(cudaStreamWaitEvent(st, h->events[L.count], 0)); continue; }
-      launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs, st);
-      nk++;
-    }
-    if (two) {
-      CUDA_OK(cudaEventRecord(h->ev_join, h->s_bulk));
-      CUDA_OK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+      if (exec != nullptr) {
+        CUDA_OK(cudaGraphLaunch(exec, h->s_main));
+      } else {
+        CUDA_OK(cudaStreamWaitEvent(h->s_bulk, h->ev_fork, 0));
+        issue_schedule(h, sch, X, vec_arena, d_vptr, nrhs, true, nullptr);
+        CUDA_OK(cudaEventRecord(h->ev_join, h->s_bulk));
+        CUDA_OK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+      }
       CUDA_OK(cudaEventRecord(h->ev_join, h->s_main));
       CUDA_OK(cudaStreamWaitEvent(0, h->ev_join, 0));
+    } else {
+      issue_schedule(h, sch, X, vec_arena, d_vptr, nrhs, false, h->cur);
     }
   } else {
     // per-launch CUDA events on the launching stream (serialises nothing: same stream order), summed per kind
+    const DevSym ds = h->devsym();
+    cudaStream_t st = h->cur;
     std::vector<const Launch*> ks;
     for (const Launch& L : sch.launches) if (is_kernel(L)) ks.push_back(&L);
     const size_t nl = ks.size();
     std::vector<cudaEvent_t> ev(nl + 1);
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
-    CUDA_OK(cudaEventRecord(ev[0], 0));
+    CUDA_OK(cudaEventRecord(ev[0], st));
     for (size_t i = 0; i < nl; i++) {
-      launch_one(h, sch, *ks[i], ds, X, vec_arena, d_vptr, nrhs, 0);
-      CUDA_OK(cudaEventRecord(ev[i + 1], 0));
+      launch_one(h, sch, *ks[i], ds, X, vec_arena, d_vptr, nrhs, st);
+      CUDA_OK(cudaEventRecord(ev[i + 1], st));
     }
     CUDA_OK(cudaEventSynchronize(ev[nl]));
     for (size_t i = 0; i < nl; i++) {
@@ -531,7 +672,6 @@ static void run_schedule(slmm_chol* h, const Schedule& sch, double* X, double* c
       h->prof_launch_grid.push_back(ks[i]->kind <= Launch::GEMM_SMALL ? ks[i]->grid : ks[i]->count);
     }
     for (auto& e : ev) cudaEventDestroy(e);
-    nk = (int64_t)nl;
   }
   g_launch_count += nk;
   CUDA_OK(cudaGetLastError());
@@ -823,10 +963,15 @@ static void build_factor_schedule(slmm_chol* h) {
 }
 
 static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
-  auto it = h->plans.find(nrhs);
+  // Plans (X / X2 / contribution arenas / split-K workspace / launch graphs) are keyed by the RHS width AND by the
+  // stream section they serve: a solve inside an auxiliary section runs beside the one on stream 0, so the two must
+  // never share buffers even when their widths coincide (c+1 == local probe width).
+  const int key = nrhs * 2 + (h->cur != nullptr ? 1 : 0);
+  auto it = h->plans.find(key);
   if (it != h->plans.end()) return it->second.get();
-  // keep at most two widths resident (probe block + deterministic RHS)
-  if (h->plans.size() >= 3) {
+  // keep a few widths resident (probe block, deterministic RHS, compute_hess stages)
+  if (h->plans.size() >= 6) {
+    CUDA_OK(cudaDeviceSynchronize());
     for (auto& kv : h->plans) kv.second->release();
     h->plans.clear();
   }
@@ -990,7 +1135,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
   pl->lmul.upload();
   pl->bytes += pl->fwd.device_bytes() + pl->bwd.device_bytes() + pl->lmul.device_bytes();
   SolvePlan* raw = pl.get();
-  h->plans[nrhs] = std::move(pl);
+  h->plans[key] = std::move(pl);
   return raw;
 }
 
@@ -1063,6 +1208,7 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
   h->d_child_idx = dev_upload(S.child_idx.data(), S.child_idx.size());
   h->d_col2sn = dev_upload(S.col2sn.data(), S.col2sn.size());
   h->d_perm = dev_upload(S.perm.data(), S.perm.size());
+  h->d_iperm = dev_upload(S.iperm.data(), S.iperm.size());
   h->d_sn_rowptr = dev_upload(S.sn_rowptr.data(), S.sn_rowptr.size());
   h->d_sn_lptr = dev_upload(S.sn_lptr.data(), S.sn_lptr.size());
   h->d_sn_uptr = dev_upload(h->uptr.data(), h->uptr.size());
@@ -1099,7 +1245,7 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
 int slmm_chol_destroy(slmm_chol_t* h) {
   if (!h) return SLMM_OK;
   dev_free(h->d_sn_first); dev_free(h->d_sn_nrow); dev_free(h->d_rows); dev_free(h->d_rel);
-  dev_free(h->d_child_ptr); dev_free(h->d_child_idx); dev_free(h->d_col2sn); dev_free(h->d_perm);
+  dev_free(h->d_child_ptr); dev_free(h->d_child_idx); dev_free(h->d_col2sn); dev_free(h->d_perm); dev_free(h->d_iperm);
   dev_free(h->d_sn_rowptr); dev_free(h->d_sn_lptr); dev_free(h->d_sn_uptr);
   dev_free(h->Lx); dev_free(h->inv); dev_free(h->W); dev_free(h->wscratch); dev_free(h->d_wblocks); dev_free(h->arena[0]); dev_free(h->arena[1]);
   dev_free(h->d_info); dev_free(h->d_partial);
@@ -1143,16 +1289,48 @@ int slmm_chol_perm(const slmm_chol_t* h, int32_t* perm) {
   SLMM_CATCH
 }
 
-int slmm_chol_register_pattern(slmm_chol_t* h, const int32_t* indptr, const int32_t* indices, int32_t* map_id) {
+int slmm_chol_register_pattern_tri(slmm_chol_t* h, const int32_t* indptr, const int32_t* indices, int32_t tri,
+                                   int32_t* map_id) {
   SLMM_TRY
   if (!h || !indptr || !indices || !map_id) throw std::invalid_argument("null argument");
   const int64_t nnz = indptr[h->S.n];
   std::vector<int64_t> tgt(nnz);
-  entry_map(h->S, indptr, indices, tgt.data());
+  entry_map(h->S, indptr, indices, tgt.data(), tri);
   EntryMap m;
   m.nnz = nnz;
   m.d_map = dev_upload(tgt.data(), tgt.size());
   CUDA_OK(cudaDeviceSynchronize());
+  h->maps.push_back(m);
+  *map_id = (int32_t)h->maps.size() - 1;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_register_pattern(slmm_chol_t* h, const int32_t* indptr, const int32_t* indices, int32_t* map_id) {
+  return slmm_chol_register_pattern_tri(h, indptr, indices, 0, map_id);
+}
+
+int slmm_chol_register_pattern_device(slmm_chol_t* h, const int32_t* d_indptr, const int32_t* d_indices, int64_t nnz,
+                                      int32_t tri, int32_t* map_id) {
+  SLMM_TRY
+  if (!h || !d_indptr || !d_indices || !map_id || nnz < 0) throw std::invalid_argument("bad arguments");
+  EntryMap m;
+  m.nnz = nnz;
+  m.d_map = dev_alloc<int64_t>((size_t)nnz);
+  int* d_bad = dev_alloc<int>(1);
+  CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), 0));
+  const int n = h->S.n;
+  entry_map_kernel<<<std::max(1, std::min(148 * 8, (n + 7) / 8)), 256>>>(d_indptr, d_indices, n, h->d_iperm, h->d_col2sn,
+                                                                       h->devsym(), tri, m.d_map, d_bad);
+  g_launch_count++;
+  int bad = 0;
+  const cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+  dev_free(d_bad);
+  if (e != cudaSuccess || bad) {
+    dev_free(m.d_map);
+    CUDA_OK(e);
+    throw std::invalid_argument("matrix entry outside the analysed pattern");
+  }
   h->maps.push_back(m);
   *map_id = (int32_t)h->maps.size() - 1;
   return SLMM_OK;
@@ -1257,6 +1435,18 @@ int slmm_chol_lmul(slmm_chol_t* h, const double* d_Z, double* d_out, int32_t nrh
   run_schedule(h, pl->lmul, pl->X2, pl->arena, pl->d_vptr, nrhs);
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
   gather_rows_kernel<<<grid, 256, 0, h->cur>>>(pl->X2, d_out, h->d_perm, n, nrhs, 1);
+  g_launch_count++;
+  CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_probe_normals(double* d_out, int64_t n, int32_t ncols, int32_t col_begin, uint64_t seed, uint64_t stream) {
+  SLMM_TRY
+  if (!d_out || n <= 0 || ncols <= 0 || col_begin < 0) throw std::invalid_argument("bad arguments");
+  const int64_t total = n * ncols;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  probe_normals_kernel<<<grid, 256>>>(d_out, n, ncols, col_begin, seed, stream);
   g_launch_count++;
   CUDA_OK(cudaGetLastError());
   return SLMM_OK;
@@ -1398,6 +1588,15 @@ int slmm_symbolic_arrays(const slmm_symbolic_t* h, int32_t* perm, int32_t* paren
   copy_out(sn_first, S.sn_first); copy_out(sn_nrow, S.sn_nrow); copy_out(sn_parent, S.sn_parent);
   copy_out(sn_rowptr, S.sn_rowptr); copy_out(sn_lptr, S.sn_lptr); copy_out(rows, S.rows); copy_out(rel, S.rel);
   copy_out(level_ptr, S.level_ptr); copy_out(level_sn, S.level_sn);
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_symbolic_entry_map_tri(const slmm_symbolic_t* h, const int32_t* indptr, const int32_t* indices, int32_t tri,
+                                int64_t* target) {
+  SLMM_TRY
+  if (!h || !indptr || !indices || !target) throw std::invalid_argument("null argument");
+  entry_map(h->S, indptr, indices, target, tri);
   return SLMM_OK;
   SLMM_CATCH
 }

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -26,6 +27,7 @@ struct CsrDev {
   uint64_t idx_hash = 0;
   int symmetric = -1;      // -1 unknown, 0 no, 1 yes (checked on the device on first use)
   int32_t* rend = nullptr; // per row: one past the last entry with col <= row (pattern leaders only, built lazily)
+  int32_t* rend_base = nullptr;   // allocation behind rend (rend is shifted by -r0 for row-block shards)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -211,10 +213,10 @@ __global__ void __launch_bounds__(256) he_short_kernel(const int32_t* __restrict
 // when the target has no such entry (or, for symmetric sets, when the entry lies above the diagonal).
 __global__ void __launch_bounds__(256) cross_map_kernel(const int32_t* __restrict__ pp, const int32_t* __restrict__ pi,
                                                         const int32_t* __restrict__ tp, const int32_t* __restrict__ ti,
-                                                        int n, int lower_only, int64_t* __restrict__ map) {
+                                                        int r0, int n, int lower_only, int64_t* __restrict__ map) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+  for (int row = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n; row += warps) {
     const int sb = pp[row], se = pp[row + 1], lb = tp[row], le = tp[row + 1];
     for (int p = sb + lane; p < se; p += 32) {
       const int col = pi[p];
@@ -621,11 +623,47 @@ __global__ void __launch_bounds__(256) symmetry_check_kernel(const int32_t* __re
   }
 }
 
+// Symmetry check for ROW-BLOCK SHARDS, where the mirror image of an entry usually lives on another GPU: every stored
+// off-diagonal entry (i, j, value bits) is hashed under the key (min, max, bits); entries above the diagonal are summed
+// (mod 2^64) into out[0], entries below into out[1].  The matrix equals its transpose exactly when the two multisets of
+// keys coincide, so after a sum over all shards out[0] == out[1] (a mismatch survives with probability ~2^-64).
+// Integer sums are order independent: the result is deterministic.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) symmetry_hash_kernel(const int32_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices,
+                                                            const double* __restrict__ data, int r0, int r1,
+                                                            unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long up = 0, lo = 0;
+  for (int row = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < r1; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    for (int p = b + lane; p < e; p += 32) {
+      const int col = indices[p];
+      if (col == row) continue;
+      const unsigned long long a = (unsigned long long)min(row, col), c = (unsigned long long)max(row, col);
+      const unsigned long long h = mix64(mix64((a << 32) | c) ^ (unsigned long long)__double_as_longlong(data[p]));
+      if (col > row) up += h; else lo += h;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    up += __shfl_xor_sync(0xffffffffu, up, o);
+    lo += __shfl_xor_sync(0xffffffffu, lo, o);
+  }
+  if (lane == 0) { atomicAdd(out, up); atomicAdd(out + 1, lo); }
+}
+
 // rend[row] = one past the last entry of the (sorted) row with col <= row
 __global__ void __launch_bounds__(256) row_end_kernel(const int32_t* __restrict__ indptr,
-                                                      const int32_t* __restrict__ indices, int n,
+                                                      const int32_t* __restrict__ indices, int r0, int n,
                                                       int32_t* __restrict__ rend) {
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+  for (int row = r0 + blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
     int lo = indptr[row], hi = indptr[row + 1];
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (indices[mid] <= row) lo = mid + 1; else hi = mid; }
     rend[row] = lo;
@@ -635,12 +673,12 @@ __global__ void __launch_bounds__(256) row_end_kernel(const int32_t* __restrict_
 // CSR sanity on the device (the host never scans the 10^8-entry index arrays): rows strictly increasing (sorted, no
 // duplicates), indices inside [0,n), row pointers monotone.  flag bits: 1 unsorted/duplicate, 2 out of range.
 __global__ void __launch_bounds__(256) csr_validate_kernel(const int32_t* __restrict__ indptr,
-                                                           const int32_t* __restrict__ indices, int n, int64_t nnz,
-                                                           int* __restrict__ flag) {
+                                                           const int32_t* __restrict__ indices, int r0, int r1, int n,
+                                                           int64_t nnz, int* __restrict__ flag) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   int bad = 0;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+  for (int row = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < r1; row += warps) {
     const int b = indptr[row], e = indptr[row + 1];
     if (b > e || b < 0 || (int64_t)e > nnz) { bad |= 2; continue; }
     for (int p = b + lane; p < e; p += 32) {
@@ -661,12 +699,31 @@ __global__ void __launch_bounds__(256) arrays_differ_kernel(const int32_t* __res
   if (bad) *flag = 1;
 }
 
+// every entry of pattern A must be present in pattern B (sorted rows): flag = 1 otherwise
+__global__ void __launch_bounds__(256) pattern_subset_kernel(const int32_t* __restrict__ ap, const int32_t* __restrict__ ai,
+                                                             const int32_t* __restrict__ bp, const int32_t* __restrict__ bi,
+                                                             int n, int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const int sb = ap[row], se = ap[row + 1], lb = bp[row], le = bp[row + 1];
+    for (int p = sb + lane; p < se; p += 32) {
+      const int col = ai[p];
+      int lo = lb, hi = le;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (bi[mid] < col) lo = mid + 1; else hi = mid; }
+      if (!(lo < le && bi[lo] == col)) *flag = 1;
+    }
+  }
+}
+
 }  // namespace slmm
 
 using namespace slmm;
 
 struct slmm_matset {
   int n = 0, K = 0;
+  int r0 = 0, r1 = 0;      // rows held by this set (a row-block shard of the HE path holds [r0, r1) only)
+  bool sharded() const { return r0 != 0 || r1 != n; }
   std::vector<CsrDev> m;
   std::map<std::pair<int, int>, int64_t*> cross_maps;   // (probe pattern, target pattern) -> position map (device)
   double* d_partial = nullptr;
@@ -781,6 +838,7 @@ int slmm_matset_create(int32_t n, int32_t K, slmm_matset_t** out) {
   std::unique_ptr<slmm_matset> ms(new slmm_matset());
   ms->n = n;
   ms->K = K;
+  ms->r1 = n;
   ms->m.resize(K);
   ms->d_y = dev_alloc<double>(n);
   ms->d_out = dev_alloc<double>(2 * K + 2 * K * K);
@@ -795,7 +853,7 @@ int slmm_matset_destroy(slmm_matset_t* ms) {
   for (auto& c : ms->m) {
     if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
     if (c.owned_data) dev_free((void*)c.data);
-    dev_free(c.rend);
+    dev_free(c.rend_base);
   }
   dev_free(ms->d_partial); dev_free(ms->d_y); dev_free(ms->d_out); dev_free(ms->d_dst);
   dev_free(ms->he_arena); dev_free(ms->d_he_desc);
@@ -810,10 +868,11 @@ int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* indptr, cons
   CsrDev& c = ms->m[k];
   if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
   if (c.owned_data) dev_free((void*)c.data);
-  dev_free(c.rend);
+  dev_free(c.rend_base);
   for (auto& kv : ms->cross_maps) dev_free(kv.second);
   ms->cross_maps.clear();
   c = CsrDev();
+  if (ms->sharded()) throw std::invalid_argument("slmm_matset_upload takes whole matrices (row-block shards bind device arrays)");
   const int n = ms->n;
   c.nnz = indptr[n];
   c.h_indptr.assign(indptr, indptr + n + 1);
@@ -847,11 +906,12 @@ int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indpt
   CsrDev& c = ms->m[k];
   if (c.owned_pattern) { dev_free((void*)c.indptr); dev_free((void*)c.indices); }
   if (c.owned_data) dev_free((void*)c.data);
-  dev_free(c.rend);
+  dev_free(c.rend_base);
   for (auto& kv : ms->cross_maps) dev_free(kv.second);
   ms->cross_maps.clear();
   c = CsrDev();
-  c.indptr = d_indptr; c.indices = d_indices; c.data = d_data; c.nnz = nnz;
+  // row-block shards: d_indptr has r1 - r0 + 1 entries counting from 0; the kernels index rows globally
+  c.indptr = d_indptr - ms->r0; c.indices = d_indices; c.data = d_data; c.nnz = nnz;
   c.pattern = same_as >= 0 ? ms->m[same_as].pattern : k;
   return SLMM_OK;
   SLMM_CATCH
@@ -873,7 +933,7 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
   SLMM_TRY
   if (!ms || !d_y || !d_out) throw std::invalid_argument("null argument");
   const int K = ms->K;
-  if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
+  if (r0 < ms->r0 || r1 > ms->r1 || r0 > r1) throw std::invalid_argument("bad row range (outside the rows this set holds)");
   for (int k = 0; k < K; k++)
     if (!ms->m[k].data) throw std::invalid_argument("matrix not set");
   CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double) * (2 * K + 2 * K * K), 0));
@@ -892,8 +952,10 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
     if (!sym_all) return nullptr;
     CsrDev& lead = ms->m[ms->m[k].pattern];
     if (!lead.rend) {
-      lead.rend = dev_alloc<int32_t>(ms->n);
-      row_end_kernel<<<std::min(148 * 8, (ms->n + 255) / 256), 256>>>(lead.indptr, lead.indices, ms->n, lead.rend);
+      const int rows = ms->r1 - ms->r0;
+      lead.rend_base = dev_alloc<int32_t>(rows);
+      lead.rend = lead.rend_base - ms->r0;
+      row_end_kernel<<<std::max(1, std::min(148 * 8, (rows + 255) / 256)), 256>>>(lead.indptr, lead.indices, ms->r0, ms->r1, lead.rend);
       g_launch_count++;
     }
     return lead.rend;
@@ -964,8 +1026,8 @@ int slmm_he_moments(slmm_matset_t* ms, const double* d_y, int32_t r0, int32_t r1
         int64_t*& map = ms->cross_maps[std::make_pair(lp, lt)];
         if (!map) {             // once per pattern pair: where every probe entry sits in the target
           map = dev_alloc<int64_t>(ms->m[lp].nnz);
-          cross_map_kernel<<<he_grid(ms->n), 256>>>(ms->m[lp].indptr, ms->m[lp].indices, ms->m[lt].indptr,
-                                                    ms->m[lt].indices, ms->n, sym_all ? 1 : 0, map);
+          cross_map_kernel<<<he_grid(ms->r1 - ms->r0), 256>>>(ms->m[lp].indptr, ms->m[lp].indices, ms->m[lt].indptr,
+                                                              ms->m[lt].indices, ms->r0, ms->r1, sym_all ? 1 : 0, map);
           g_launch_count++;
         }
         const int64_t pn = ms->m[lp].nnz;
@@ -1027,6 +1089,7 @@ int slmm_he_moments_host(slmm_matset_t* ms, const double* h_y, double* h_out) {
 static int spmm_impl(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t ncols, int32_t r0, int32_t r1,
                      double* d_out, bool dot) {
   if (!ms || k < 0 || k >= ms->K || !d_X || !d_out || ncols <= 0) throw std::invalid_argument("bad arguments");
+  if (ms->sharded()) throw std::invalid_argument("row-block shards serve slmm_he_moments only");
   if (ncols > 256) throw std::invalid_argument("at most 256 columns per call");
   if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
   const CsrDev& c = ms->m[k];
@@ -1067,6 +1130,7 @@ int slmm_spmm_coldot_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, con
   if (!ms || !ks || !d_X || !d_dots || nk <= 0 || nk > 2 || ncols <= 0 || ncols > 160)
     throw std::invalid_argument("slmm_spmm_coldot_multi: need 1 <= nk <= 2, ncols <= 160");
   if (store_from < 0 || store_from > ncols || (store_from < ncols && !d_store)) throw std::invalid_argument("bad store range");
+  if (ms->sharded()) throw std::invalid_argument("row-block shards serve slmm_he_moments only");
   if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
   for (int g = 0; g < nk; g++) {
     if (ks[g] < 0 || ks[g] >= ms->K || !ms->m[ks[g]].data) throw std::invalid_argument("matrix not set");
@@ -1090,7 +1154,7 @@ int slmm_matset_validate(slmm_matset_t* ms, int32_t k, int32_t* flags_out) {
   const CsrDev& c = ms->m[k];
   int* d_flag = dev_alloc<int>(1);
   CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
-  csr_validate_kernel<<<he_grid(ms->n), 256>>>(c.indptr, c.indices, ms->n, c.nnz, d_flag);
+  csr_validate_kernel<<<he_grid(ms->r1 - ms->r0), 256>>>(c.indptr, c.indices, ms->r0, ms->r1, ms->n, c.nnz, d_flag);
   g_launch_count++;
   int flag = 0;
   CUDA_OK(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1122,6 +1186,7 @@ int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out) {
   SLMM_TRY
   if (!ms || k < 0 || k >= ms->K || !out || !ms->m[k].data) throw std::invalid_argument("bad arguments");
   CsrDev& c = ms->m[k];
+  if (c.symmetric < 0 && ms->sharded()) { *out = 0; return SLMM_OK; }   // unknown until slmm_matset_set_symmetric
   if (c.symmetric < 0) {
     int* d_flag = dev_alloc<int>(1);
     CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
@@ -1175,6 +1240,7 @@ int slmm_quadform_gram_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, c
   if (!ms || !ks || !d_X || !d_dots || nk <= 0 || nk > 2 || ncols <= 0 || ncols > 160)
     throw std::invalid_argument("slmm_quadform_gram_multi: need 1 <= nk <= 2, ncols <= 160");
   if (d_XB && (nb <= 0 || nb > QF_NB || !d_gram_half)) throw std::invalid_argument("narrow block: 1 <= nb <= 16");
+  if (ms->sharded()) throw std::invalid_argument("row-block shards serve slmm_he_moments only");
   if (r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
   bool sym = true;
   for (int g = 0; g < nk; g++) {
@@ -1197,6 +1263,151 @@ int slmm_quadform_gram_multi(slmm_matset_t* ms, int32_t nk, const int32_t* ks, c
   else if (cpl <= 4) { QF_CASE(4) } else { QF_CASE(5) }
 #undef QF_CASE
   CUDA_OK(cudaGetLastError());
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_device_csr_is_symmetric(const int32_t* d_indptr, const int32_t* d_indices, const double* d_data, int32_t n,
+                                 int32_t* out) {
+  SLMM_TRY
+  if (!d_indptr || !d_indices || !d_data || !out || n <= 0) throw std::invalid_argument("bad arguments");
+  int* d_flag = dev_alloc<int>(1);
+  CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
+  symmetry_check_kernel<<<he_grid(n), 256>>>(d_indptr, d_indices, d_data, n, d_flag);
+  g_launch_count++;
+  int flag = 1;
+  const cudaError_t e = cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  dev_free(d_flag);
+  CUDA_OK(e);
+  *out = flag ? 0 : 1;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_device_pattern_subset(const int32_t* d_ap, const int32_t* d_ai, const int32_t* d_bp, const int32_t* d_bi,
+                               int32_t n, int32_t* out) {
+  SLMM_TRY
+  if (!d_ap || !d_ai || !d_bp || !d_bi || !out || n <= 0) throw std::invalid_argument("bad arguments");
+  int* d_flag = dev_alloc<int>(1);
+  CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), 0));
+  pattern_subset_kernel<<<he_grid(n), 256>>>(d_ap, d_ai, d_bp, d_bi, n, d_flag);
+  g_launch_count++;
+  int flag = 1;
+  const cudaError_t e = cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  dev_free(d_flag);
+  CUDA_OK(e);
+  *out = flag ? 0 : 1;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_set_row_range(slmm_matset_t* ms, int32_t r0, int32_t r1) {
+  SLMM_TRY
+  if (!ms || r0 < 0 || r1 > ms->n || r0 > r1) throw std::invalid_argument("bad row range");
+  for (const CsrDev& c : ms->m)
+    if (c.data) throw std::invalid_argument("set the row range before binding matrices");
+  ms->r0 = r0;
+  ms->r1 = r1;
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_symmetry_hash(slmm_matset_t* ms, int32_t k, uint64_t* h_out2) {
+  SLMM_TRY
+  if (!ms || k < 0 || k >= ms->K || !h_out2 || !ms->m[k].data) throw std::invalid_argument("bad arguments");
+  const CsrDev& c = ms->m[k];
+  unsigned long long* d = dev_alloc<unsigned long long>(2);
+  CUDA_OK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), 0));
+  symmetry_hash_kernel<<<he_grid(ms->r1 - ms->r0), 256>>>(c.indptr, c.indices, c.data, ms->r0, ms->r1, d);
+  g_launch_count++;
+  const cudaError_t e = cudaMemcpy(h_out2, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  dev_free(d);
+  CUDA_OK(e);
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_matset_set_symmetric(slmm_matset_t* ms, int32_t k, int32_t flag) {
+  if (!ms || k < 0 || k >= ms->K) return SLMM_ERR_INVALID;
+  ms->m[k].symmetric = flag ? 1 : 0;
+  return SLMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host -> device copies of large PAGEABLE arrays (the scipy CSR arrays the reference API hands us).  cudaMemcpy from
+// pageable memory runs at a fraction of the link rate and Tensor.pin_memory() first copies the whole array into a
+// freshly page-locked allocation (page-locking is the slow part).  Here a few worker threads copy chunks into a
+// small ring of PERSISTENT pinned buffers and queue the DMA of each chunk as soon as it is staged, so the host copy
+// of chunk i+1 overlaps the transfer of chunk i and nothing is page-locked per call.
+namespace {
+struct Stager {
+  static constexpr int MAXT = 8, RING = 2;
+  static constexpr size_t CHUNK = (size_t)8 << 20;
+  void* buf[MAXT][RING] = {};
+  cudaEvent_t ev[MAXT][RING] = {};
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t st = nullptr;
+  int device = -1;
+  void init(int T) {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (st == nullptr || dev != device) {
+      device = dev;
+      CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    }
+    for (int t = 0; t < T; t++)          // page-locked once per process, only for the workers actually used
+      for (int r = 0; r < RING; r++)
+        if (buf[t][r] == nullptr) {
+          CUDA_OK(cudaHostAlloc(&buf[t][r], CHUNK, cudaHostAllocDefault));
+          CUDA_OK(cudaEventCreateWithFlags(&ev[t][r], cudaEventDisableTiming));
+        }
+  }
+};
+Stager g_stager;
+}  // namespace
+
+int slmm_upload_h2d(void* d_dst, const void* h_src, int64_t nbytes, int32_t threads) {
+  SLMM_TRY
+  if (!d_dst || !h_src || nbytes < 0) throw std::invalid_argument("bad arguments");
+  if (nbytes == 0) return SLMM_OK;
+  if (nbytes < (int64_t)(4 << 20)) {            // small arrays: the driver's own staging is as good
+    CUDA_OK(cudaMemcpyAsync(d_dst, h_src, (size_t)nbytes, cudaMemcpyHostToDevice, 0));
+    return SLMM_OK;
+  }
+  Stager& S = g_stager;
+  const int T = std::max(1, std::min<int>(Stager::MAXT, threads > 0 ? threads : 4));
+  S.init(T);
+  const int64_t nchunks = (nbytes + (int64_t)Stager::CHUNK - 1) / (int64_t)Stager::CHUNK;
+  int dev = S.device;
+  // the destination may be recycled memory with work still queued on the default stream
+  CUDA_OK(cudaEventRecord(S.ev_in, 0));
+  CUDA_OK(cudaStreamWaitEvent(S.st, S.ev_in, 0));
+  std::vector<cudaError_t> err(T, cudaSuccess);
+  auto work = [&](int t) {
+    cudaError_t e = cudaSetDevice(dev);
+    int use = 0;
+    for (int64_t c = t; c < nchunks && e == cudaSuccess; c += T, use++) {
+      const int r = use % Stager::RING;
+      const size_t off = (size_t)c * Stager::CHUNK, sz = std::min<size_t>(Stager::CHUNK, (size_t)nbytes - off);
+      if (use >= Stager::RING) e = cudaEventSynchronize(S.ev[t][r]);      // the DMA that last used this buffer is done
+      if (e != cudaSuccess) break;
+      memcpy(S.buf[t][r], (const char*)h_src + off, sz);
+      e = cudaMemcpyAsync((char*)d_dst + off, S.buf[t][r], sz, cudaMemcpyHostToDevice, S.st);
+      if (e == cudaSuccess) e = cudaEventRecord(S.ev[t][r], S.st);
+    }
+    err[t] = e;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < T; t++) CUDA_OK(err[t]);
+  CUDA_OK(cudaEventRecord(S.ev_out, S.st));
+  CUDA_OK(cudaStreamWaitEvent(0, S.ev_out, 0));
+  // the staging buffers are reused by the next call: its first writes must not overtake this call's last DMAs
+  CUDA_OK(cudaEventSynchronize(S.ev_out));
   return SLMM_OK;
   SLMM_CATCH
 }

@@ -491,13 +491,26 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
   S.t_symbolic = now_s() - t0;
 }
 
-void entry_map(const Symbolic& S, const int32_t* ap, const int32_t* ai, int64_t* target) {
+void entry_map(const Symbolic& S, const int32_t* ap, const int32_t* ai, int64_t* target, int tri) {
+  // tri == 0: both triangles are stored with identical values (verified by the caller): the copy that lands on or
+  //           below the diagonal AFTER the permutation carries the value, its mirror image is skipped.
+  // tri != 0: CHOLMOD semantics - only one stored triangle defines the matrix (sksparse reads the lower triangle of
+  //           the CSC matrix it is given): tri > 0 keeps the entries with index >= row of the given arrays (the lower
+  //           triangle when the arrays are CSC), tri < 0 those with index <= row (the lower triangle of a CSR
+  //           matrix); each kept entry is placed at (max, min) of its permuted coordinates.
   const int n = S.n;
   for (int r = 0; r < n; r++) {
-    const int ir = S.iperm[r];
+    const int pr = S.iperm[r];
     for (int p = ap[r]; p < ap[r + 1]; p++) {
-      const int ic = S.iperm[ai[p]];
-      if (ic > ir) { target[p] = -1; continue; }      // mirrored copy carries the value
+      const int c = ai[p];
+      const int pc = S.iperm[c];
+      int ir = pr, ic = pc;
+      if (tri == 0) {
+        if (ic > ir) { target[p] = -1; continue; }    // mirrored copy carries the value
+      } else {
+        if ((tri > 0 && c < r) || (tri < 0 && c > r)) { target[p] = -1; continue; }
+        if (ic > ir) { ir = pc; ic = pr; }
+      }
       // entry (row ir, col ic) with ir >= ic lives in the panel of ic's supernode
       const int s = S.col2sn[ic];
       const int f = S.sn_first[s];

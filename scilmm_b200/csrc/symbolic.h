@@ -60,7 +60,8 @@ void analyze(int n, const int32_t* indptr, const int32_t* indices, const int32_t
 // position map of original matrix entries into the panel storage.
 // (rowidx_of_entry, colidx_of_entry) are given as a CSR/CSC pattern (symmetric => orientation is immaterial);
 // target[e] = offset into panel storage for the copy with new_row >= new_col, -1 for the mirrored copy.
+// tri != 0 selects CHOLMOD's one-triangle semantics (see the definition).
 // Entries outside the analysed pattern raise std::runtime_error.
-void entry_map(const Symbolic& S, const int32_t* indptr, const int32_t* indices, int64_t* target);
+void entry_map(const Symbolic& S, const int32_t* indptr, const int32_t* indices, int64_t* target, int tri = 0);
 
 }  // namespace slmm

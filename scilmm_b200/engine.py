@@ -50,15 +50,19 @@ def canonical_csr(m):
     return m
 
 
+UPLOAD_THREADS = 4          # worker threads of the staged upload (lowered when several ranks share the host's cores)
+
+
 def to_device(a, torch=None):
-    """Host ndarray -> CUDA tensor through pinned staging (fast H2D)."""
+    """Host ndarray -> CUDA tensor.  Large pageable arrays go through the library's ring of persistent pinned
+    buffers (slmm_upload_h2d: no per-call page-locking, host copy overlapped with the DMA)."""
     torch = torch or require_cuda()
-    t = torch.from_numpy(np.ascontiguousarray(a))
-    try:
-        t = t.pin_memory()
-    except RuntimeError:
-        pass
-    return t.to("cuda", non_blocking=True)
+    a = np.ascontiguousarray(a)
+    if a.nbytes < (4 << 20):
+        return torch.from_numpy(a).to("cuda", non_blocking=False)
+    out = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].reshape(-1)).dtype, device="cuda")
+    check(lib().slmm_upload_h2d(out.data_ptr(), np_ptr(a), int(a.nbytes), int(UPLOAD_THREADS)))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ symbolic
@@ -112,19 +116,25 @@ class SymbolicView(object):
 
 
 # ------------------------------------------------------------------------------------------------ matrices
-def _csr_arrays(m):
+def _csr_arrays(m, row_range=None):
     """(indptr, indices, data, nnz) of a scipy CSR matrix as int32/int32/float64 contiguous arrays WITHOUT scanning
-    them on the host (sortedness and ranges are verified on the device after the upload)."""
+    them on the host (sortedness and ranges are verified on the device after the upload).  row_range = (r0, r1)
+    takes the slices of a row block: indptr counted from 0, views of indices / data (no copy)."""
     if not sp.isspmatrix_csr(m):
         m = sp.csr_matrix(m)
     ip, ix, dt = m.indptr, m.indices, m.data
+    if row_range is not None and tuple(row_range) != (0, m.shape[0]):
+        r0, r1 = row_range
+        a, b = int(ip[r0]), int(ip[r1])
+        ip = (ip[r0:r1 + 1] - ip[r0]).astype(np.int32)
+        ix, dt = ix[a:b], dt[a:b]
     if ip.dtype != np.int32:
         ip = ip.astype(np.int32)
     if ix.dtype != np.int32:
         ix = ix.astype(np.int32)
     if dt.dtype != np.float64:
         dt = dt.astype(np.float64)
-    return np.ascontiguousarray(ip), np.ascontiguousarray(ix), np.ascontiguousarray(dt), int(m.nnz)
+    return np.ascontiguousarray(ip), np.ascontiguousarray(ix), np.ascontiguousarray(dt), int(ix.size)
 
 
 class MatSet(object):
@@ -134,13 +144,19 @@ class MatSet(object):
     Hadamard square) is decided by an exact comparison ON THE DEVICE, and so is the CSR sanity check (sorted rows,
     indices in range); a matrix that fails it is canonicalised by scipy and uploaded again."""
 
-    def __init__(self, mats):
+    def __init__(self, mats, row_range=None):
+        """row_range = (r0, r1): a ROW-BLOCK SHARD of the HE path - only rows [r0, r1) of every matrix are uploaded
+        and held; such a set serves he_moments_device only."""
         torch = require_cuda()
         self.n = mats[0].shape[0]
         self.K = len(mats)
+        self.row_range = (0, self.n) if row_range is None else (int(row_range[0]), int(row_range[1]))
         h = C.c_void_p()
         check(lib().slmm_matset_create(self.n, self.K, C.byref(h)))
         self._h = h
+        if self.row_range != (0, self.n):
+            check(lib().slmm_matset_set_row_range(h, self.row_range[0], self.row_range[1]))
+        self._sym_known = self.row_range == (0, self.n)
         self._keep = []
         self.nnz = []
         self.h2d_bytes = 0
@@ -152,7 +168,7 @@ class MatSet(object):
         self._out = torch.zeros(2 * self.K + 2 * self.K * self.K, dtype=torch.float64, device="cuda")
 
     def _bind(self, k, m, patterns, torch, verified):
-        ip, ix, dt, nnz = _csr_arrays(m)
+        ip, ix, dt, nnz = _csr_arrays(m, self.row_range)
         dat_t = to_device(dt, torch)
         self.h2d_bytes += dt.nbytes
         same = -1
@@ -181,6 +197,8 @@ class MatSet(object):
             if flags.value & 2:
                 raise ValueError("matrix %d: CSR indices / row pointers out of range" % k)
             if flags.value & 1:       # unsorted rows or duplicates: let scipy canonicalise, upload again
+                if self.row_range != (0, self.n):
+                    raise ValueError("matrix %d: row-block shards need canonical CSR (sorted rows, no duplicates)" % k)
                 mc = sp.csr_matrix(m).copy()
                 mc.sum_duplicates()
                 return self._bind(k, canonical_csr(mc), patterns, torch, verified=True)
@@ -196,9 +214,38 @@ class MatSet(object):
     def values_ptr(self, k):
         return self._keep[k][2].data_ptr()
 
-    def he_moments_device(self, y_dev, row_begin=0, row_end=None):
+    def device_arrays(self, k):
+        """(indptr, indices, data) torch tensors of matrix k in HBM."""
+        return self._keep[k]
+
+    def pattern_is_subset(self, k_small, k_big):
+        """True when every stored entry of matrix k_small is also stored in matrix k_big (device check)."""
+        a, b = self._keep[k_small], self._keep[k_big]
+        if a[1].data_ptr() == b[1].data_ptr():
+            return True
+        return device_pattern_subset(a[0], a[1], b[0], b[1], self.n)
+
+    def resolve_symmetry_sharded(self, allreduce_sum_):
+        """Row-block shards cannot see the mirror image of their entries: every rank hashes its entries above / below
+        the diagonal (slmm_matset_symmetry_hash), the two 64-bit sums are added over ranks (wrapping) and compared.
+        COLLECTIVE: every rank of the group must call it.  Without it the shard reads full rows (still correct)."""
+        if self._sym_known:
+            return
+        torch = _torch()
+        h = np.zeros(2 * self.K, dtype=np.uint64)
+        for k in range(self.K):
+            check(lib().slmm_matset_symmetry_hash(self._h, k, np_ptr(h[2 * k:2 * k + 2])))
+        t = torch.from_numpy(h.view(np.int64).copy()).to("cuda")
+        allreduce_sum_(t)
+        tot = t.cpu().numpy()
+        for k in range(self.K):
+            check(lib().slmm_matset_set_symmetric(self._h, k, 1 if tot[2 * k] == tot[2 * k + 1] else 0))
+        self._sym_known = True
+
+    def he_moments_device(self, y_dev, row_begin=None, row_end=None):
         """Partial moments of rows [row_begin,row_end) as a device tensor (layout: include/scilmm_b200.h)."""
-        row_end = self.n if row_end is None else row_end
+        row_begin = self.row_range[0] if row_begin is None else row_begin
+        row_end = self.row_range[1] if row_end is None else row_end
         check(lib().slmm_he_moments(self._h, y_dev.data_ptr(), int(row_begin), int(row_end), self._out.data_ptr()))
         return self._out
 
@@ -329,6 +376,19 @@ class MatSet(object):
             pass
 
 
+def device_csr_is_symmetric(ptr_t, idx_t, dat_t, n):
+    v = C.c_int32(0)
+    check(lib().slmm_device_csr_is_symmetric(ptr_t.data_ptr(), idx_t.data_ptr(), dat_t.data_ptr(), int(n), C.byref(v)))
+    return bool(v.value)
+
+
+def device_pattern_subset(ap_t, ai_t, bp_t, bi_t, n):
+    v = C.c_int32(0)
+    check(lib().slmm_device_pattern_subset(ap_t.data_ptr(), ai_t.data_ptr(), bp_t.data_ptr(), bi_t.data_ptr(), int(n),
+                                           C.byref(v)))
+    return bool(v.value)
+
+
 # ------------------------------------------------------------------------------------------------ factor
 class CholEngine(object):
     """Symbolic analysis + device-resident supernodal factor (slmm_chol_t)."""
@@ -362,11 +422,20 @@ class CholEngine(object):
             self._perm = p
         return self._perm
 
-    def register_pattern(self, pattern):
+    def register_pattern(self, pattern, tri=0):
+        """Scatter map of a host pattern.  tri: 0 = both triangles stored with equal values (verified by the
+        caller); +1 / -1 = CHOLMOD's rule, only the lower triangle of the CSC / CSR arrays defines the matrix."""
         pattern = canonical_csr(pattern)
         mid = C.c_int32(-1)
-        check(lib().slmm_chol_register_pattern(self._h, np_ptr(pattern.indptr), np_ptr(pattern.indices),
-                                               C.byref(mid)))
+        check(lib().slmm_chol_register_pattern_tri(self._h, np_ptr(pattern.indptr), np_ptr(pattern.indices),
+                                                   int(tri), C.byref(mid)))
+        return mid.value
+
+    def register_pattern_device(self, ptr_t, idx_t, nnz, tri=0):
+        """Same from device-resident CSR arrays (torch int32 tensors): the map is built by a kernel."""
+        mid = C.c_int32(-1)
+        check(lib().slmm_chol_register_pattern_device(self._h, ptr_t.data_ptr(), idx_t.data_ptr(), int(nnz),
+                                                      int(tri), C.byref(mid)))
         return mid.value
 
     def add_values(self, map_id, values_ptr, sigma, first):
@@ -401,6 +470,14 @@ class CholEngine(object):
         out = torch.empty_like(Z2)
         check(lib().slmm_chol_lmul(self._h, Z2.data_ptr(), out.data_ptr(), int(Z2.shape[1])))
         return out if Z.dim() == 2 else out[:, 0]
+
+    def probe_normals(self, n, ncols, col_begin, seed, stream):
+        """Columns [col_begin, col_begin+ncols) of the N(0,1) probe block of evaluation `stream` (device tensor)."""
+        torch = _torch()
+        out = torch.empty(int(n), int(ncols), dtype=torch.float64, device="cuda")
+        check(lib().slmm_probe_normals(out.data_ptr(), int(n), int(ncols), int(col_begin), int(seed) & (2 ** 64 - 1),
+                                       int(stream) & (2 ** 64 - 1)))
+        return out
 
     def aux_begin(self):
         check(lib().slmm_chol_aux_begin(self._h))

@@ -22,3 +22,10 @@ def golden_small():
 def golden_c1mini():
     from tests.util import load_golden
     return load_golden("case_c1mini")
+
+
+@pytest.fixture(scope="session")
+def golden_c1():
+    """BASELINE.json config 1 at its stated size: simulate_tree(10000, 1e-3, 1.4, 0.8) -> 7,108 individuals."""
+    from tests.util import load_golden
+    return load_golden("case_c1")

@@ -113,3 +113,35 @@ def test_legacy_entry_points_vs_reference(golden_small):
     assert rel_err(out["covariates coefficients"], ref["lmm_beta"]) < 1e-6
     assert rel_err(out["covariance std"], ref["lmm_se"]) < 1e-5
     assert rel_err(out["covariates p-values"], ref["lmm_pvalues"]) < 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_minque_two_iterations(case, request):
+    """oracle restatement of MINQUE (reference :284-347) against the unmodified reference, frozen stream, P = I."""
+    g = request.getfixturevalue(case)
+    for tag in ("k1", "k3"):
+        np.random.seed(g.seed + 6)
+        est = orc.minque(lambda M: DenseFactor(M), g.mats(tag), g["cov"], g["y"].copy(), num_iter=2,
+                         sim_num=g.sim_num)
+        assert rel_err(est, g["minque_" + tag]) < 1e-9
+
+
+def test_c1_at_stated_size(golden_c1):
+    """Config 1 at n_sim = 10,000 (7,108 individuals kept): HE, assembly bit-exactness and one REML evaluation of the
+    restatement against the unmodified reference (the dense LAPACK factor takes ~1 s at this size)."""
+    g = golden_c1
+    assert g.n == 7108 and g.csr("A").nnz == 105418
+    for tag in ("k1", "k3"):
+        est = orc.he_regression(g.mats(tag), g["cov"], g["y"].copy(), compute_stderr=False)
+        assert rel_err(est, g["he_" + tag]) < 1e-12
+    mats, sig = g.mats("k2"), g["sig_k2"]
+    ys = g["y"] / g["y"].std()
+    V = orc.weighted_sum(mats, sig)
+    V.sort_indices()
+    Vg = g.csc("V_k2")
+    assert np.array_equal(V.indptr, Vg.indptr) and np.array_equal(V.indices, Vg.indices)
+    assert np.array_equal(V.data, Vg.data)
+    np.random.seed(g.seed + 4)
+    nll, grad = orc.reml_evaluation(np.log(sig), lambda M: DenseFactor(M), mats, g["cov"], ys, True, g.sim_num)
+    assert abs(nll - g["bolt_nll_k2_1"]) < 1e-12 * abs(nll)
+    assert rel_err(grad, g["bolt_grad_k2_1"]) < 1e-9

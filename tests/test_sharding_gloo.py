@@ -102,3 +102,18 @@ def test_partition_helpers_edge_cases():
         b = sharding.row_blocks_by_nnz(indptr, w)
         assert b.size == w + 1 and b[0] == 0 and b[-1] == 6 and np.all(np.diff(b) >= 0)
     assert sharding.row_blocks_by_nnz(np.zeros(5, dtype=np.int32), 3).tolist() == [0, 0, 0, 4]
+
+
+def test_row_blocks_balance_the_lower_triangle():
+    """HE row blocks are cut by the entries on/below the diagonal (what the symmetric kernels read)."""
+    import scipy.sparse as sp
+    from scilmm_b200 import sharding
+    from tests.util import load_golden
+    A = load_golden("case_c1").csr("A")
+    low = sp.tril(A).tocsr()
+    for world in (2, 4, 8):
+        b = sharding.row_blocks_by_lower_nnz(A, world)
+        assert b[0] == 0 and b[-1] == A.shape[0] and np.all(np.diff(b) >= 0)
+        work = np.array([low.indptr[b[i + 1]] - low.indptr[b[i]] for i in range(world)], dtype=float)
+        assert work.max() / work.mean() < 1.10
+    assert list(sharding.row_blocks_by_lower_nnz(A, 1)) == [0, A.shape[0]]

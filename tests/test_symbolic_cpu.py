@@ -10,6 +10,7 @@ import scipy.linalg as la
 import scipy.sparse as sp
 
 from scilmm_b200 import _lib
+from scilmm_b200 import engine as E
 from scilmm_b200.engine import SymbolicView
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -149,3 +150,57 @@ def test_tuned_ordering_beats_metis_defaults(monkeypatch):
     monkeypatch.setenv("SLMM_RELAX", "0,0,0,0,0,0")               # no amalgamation: fundamental supernodes only
     fund = E.SymbolicView(A, ordering="metis")
     assert fund.nsuper > tuned.nsuper and fund.flops == tuned.flops and fund.lsize < tuned.lsize
+
+
+@pytest.mark.parametrize("case,tag", [("golden_small", "k4"), ("golden_c1mini", "k4"), ("golden_c1", "k2")])
+def test_independent_symbolic_agrees_with_product(case, tag, request):
+    """oracle/symbolic_ref.py (textbook etree / row-subtree counts in oracle/cpu_kernels.c, no product code) against
+    the product's host analysis on the same permutation: elimination tree, column counts, nnz(L), flops - and the
+    LAPACK multifrontal factor built on the independent structure against dense Cholesky."""
+    from oracle.cpu_factor import DenseFactor
+    from oracle.supernodal_cpu import SupernodalCPUFactor
+    from oracle.symbolic_ref import IndependentPlan
+    g = request.getfixturevalue(case)
+    V = g.csc("V_" + tag)
+    sym = SymbolicView(V, ordering="metis")
+    a = sym.arrays()
+    ip = IndependentPlan(V, a['perm'])
+    assert np.array_equal(ip.parent, a['parent'])
+    assert np.array_equal(ip.colcount, a['colcount'])
+    assert ip.sym.nnzL == sym.nnzL and ip.sym.flops == sym.flops
+    assert ip.sym.nsuper >= sym.nsuper                   # no relaxed amalgamation on the oracle side
+    f = SupernodalCPUFactor(V, plan=ip)
+    if g.n <= 2000:
+        d = DenseFactor(V, a['perm'])
+        b = np.random.default_rng(0).standard_normal((g.n, 3))
+        assert abs(f.logdet() - d.logdet()) < 1e-12 * abs(d.logdet())
+        assert np.max(np.abs(f(b) - d(b))) < 1e-11 * np.max(np.abs(d(b)))
+        assert abs(f.L() - d.L()).max() < 1e-12
+    else:
+        assert abs(f.logdet() - g["logdet_" + tag]) < 1e-11 * abs(g["logdet_" + tag])
+        assert np.max(np.abs(f(g["y"] / g["y"].std()) - g["Viy_" + tag])) < 1e-10 * np.max(np.abs(g["Viy_" + tag]))
+
+
+def test_entry_map_triangle_rules(golden_small):
+    """tri = 0 (both triangles, mirrored copy skipped) and CHOLMOD's one-triangle rules tri = +1 / -1 place the same
+    values at the same panel offsets for a symmetric matrix; the other triangle is ignored."""
+    import ctypes as C
+    from scilmm_b200._lib import check, lib, np_ptr
+    V = golden_small.csc("V_k4")
+    pat = E.canonical_csr(sp.csr_matrix((V.data, V.indices, V.indptr), shape=V.shape))
+    sym = SymbolicView(pat, ordering="metis")
+    panels = []
+    for tri in (0, 1, -1):
+        tgt = np.zeros(pat.nnz, dtype=np.int64)
+        check(lib().slmm_symbolic_entry_map_tri(sym._h, np_ptr(pat.indptr), np_ptr(pat.indices), tri, np_ptr(tgt)))
+        rows = np.repeat(np.arange(pat.shape[0]), np.diff(pat.indptr))
+        if tri > 0:
+            assert np.all((tgt >= 0) == (pat.indices >= rows))
+        if tri < 0:
+            assert np.all((tgt >= 0) == (pat.indices <= rows))
+        Lx = np.zeros(sym.lsize)
+        ok = tgt >= 0
+        assert np.unique(tgt[ok]).size == ok.sum()
+        Lx[tgt[ok]] = pat.data[ok]
+        panels.append(Lx)
+    assert np.array_equal(panels[0], panels[1]) and np.array_equal(panels[0], panels[2])
