@@ -196,6 +196,16 @@ int slmm_chol_copy_panels(slmm_chol_t* h, double* host_out);
 int slmm_launch_count(int64_t* out, int32_t reset);
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on);
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6);
+/* Timeline mode: the factorization's two-stream schedule is issued with TIMED events; after a factorization
+ * slmm_chol_get_timeline returns, per event of the schedule, the ms since the fork and the stream that recorded it
+ * (0 chain / 1 bulk; entry 0 = fork, entry 1 = join).  Shows whether the panel chain or the bulk updates are the
+ * critical path of each outer block. */
+int slmm_chol_set_timeline(slmm_chol_t* h, int32_t on);
+int slmm_chol_get_timeline(slmm_chol_t* h, int32_t max_n, int32_t* n_out, float* ms, int32_t* stream);
+/* ... and per kernel launch of that run: completion time (ms since the fork), stream, kind (as in the profile),
+ * CTAs / items, dense flops */
+int slmm_chol_get_launch_timeline(slmm_chol_t* h, int32_t max_n, int32_t* n_out, float* end_ms, int32_t* stream,
+                                  int32_t* kind, int32_t* grid, double* flops);
 /* per-launch records of the profiled runs (time, issued flops, kind, CTAs or work items); *n_out = available */
 int slmm_chol_get_launch_profile(const slmm_chol_t* h, int64_t max_n, int64_t* n_out, float* ms, double* flops,
                                  int32_t* kind, int32_t* grid);
@@ -216,6 +226,22 @@ int slmm_symbolic_entry_map(const slmm_symbolic_t* s, const int32_t* h_indptr, c
                             int64_t* h_target);
 int slmm_symbolic_entry_map_tri(const slmm_symbolic_t* s, const int32_t* h_indptr, const int32_t* h_indices,
                                 int32_t tri, int64_t* h_target);
+
+/* ------------------------------------------------------------------ IBD matrix construction ----------- */
+/* The step before the path: numerator relationship matrix from a child -> parents matrix, replacing
+ * Matrices/Numerator.py LD() :5-34 (per-individual Python loop) and create_numerator() :37-38 (L D L').  h_rel_*:
+ * host CSR of the boolean relationship matrix (row = child, columns = its <= 2 parents, parents precede children -
+ * the output of Relationship.topo_sort).  Bit-identical to the reference (same operation order, no FMA). */
+typedef struct slmm_ibd slmm_ibd_t;
+int slmm_ibd_build(int32_t n, const int32_t* h_rel_indptr, const int32_t* h_rel_indices, slmm_ibd_t** out);
+int slmm_ibd_sizes(const slmm_ibd_t* h, int64_t* nnz_L, int64_t* nnz_A, int32_t* nlevels);
+/* L of LD() (row i: 1 on the diagonal, path weights to its ancestors), sorted CSR */
+int slmm_ibd_copy_L(const slmm_ibd_t* h, int32_t* h_indptr, int32_t* h_indices, double* h_data);
+/* diagonal of D and the inbreeding coefficients F (either may be NULL) */
+int slmm_ibd_copy_DF(const slmm_ibd_t* h, double* h_D, double* h_F);
+/* A = L D L' (create_numerator), sorted CSR, both triangles */
+int slmm_ibd_copy_A(const slmm_ibd_t* h, int32_t* h_indptr, int32_t* h_indices, double* h_data);
+int slmm_ibd_destroy(slmm_ibd_t* h);
 
 /* FP64 DMMA self-test / microbenchmark of the tile GEMM (C = A B^T, column-major); returns elapsed ms */
 int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,

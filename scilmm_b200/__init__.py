@@ -10,5 +10,6 @@ from .SparseCholesky import (HE, MINQUE, REML, B200Factor, NotPositiveDefiniteEr
                              run_estimates_from_paths, simulate_vector)
 
 from .legacy import LMM, compute_HE  # noqa: F401,E402  (reference scilmm/Estimation/LMM.py:154, HE.py:22)
+from .matrices import load_sparse_csr, pairwise_epistasis, save_sparse_csr  # noqa: F401,E402  (Matrices/*.py)
 
 __version__ = "0.1.0"

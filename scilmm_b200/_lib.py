@@ -77,6 +77,9 @@ SIGNATURES = {
     "slmm_chol_aux_join": (C.c_int, [vp]),
     "slmm_launch_count": (C.c_int, [C.POINTER(i64), i32]),
     "slmm_chol_set_profiling": (C.c_int, [vp, i32]),
+    "slmm_chol_set_timeline": (C.c_int, [vp, i32]),
+    "slmm_chol_get_timeline": (C.c_int, [vp, i32, C.POINTER(i32), vp, vp]),
+    "slmm_chol_get_launch_timeline": (C.c_int, [vp, i32, C.POINTER(i32), vp, vp, vp, vp, vp]),
     "slmm_chol_get_profile": (C.c_int, [vp, vp, vp, vp]),
     "slmm_chol_get_launch_profile": (C.c_int, [vp, i64, C.POINTER(i64), vp, vp, vp, vp]),
     "slmm_symbolic_create": (C.c_int, [i32, vp, vp, i32, vp, pp]),
@@ -84,6 +87,12 @@ SIGNATURES = {
     "slmm_symbolic_stats": (C.c_int, [vp, vp, vp]),
     "slmm_symbolic_arrays": (C.c_int, [vp] + [vp] * 12),
     "slmm_symbolic_entry_map": (C.c_int, [vp, vp, vp, vp]),
+    "slmm_ibd_build": (C.c_int, [i32, vp, vp, pp]),
+    "slmm_ibd_sizes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
+    "slmm_ibd_copy_L": (C.c_int, [vp, vp, vp, vp]),
+    "slmm_ibd_copy_DF": (C.c_int, [vp, vp, vp]),
+    "slmm_ibd_copy_A": (C.c_int, [vp, vp, vp, vp]),
+    "slmm_ibd_destroy": (C.c_int, [vp]),
     "slmm_gemm_selftest": (C.c_int, [i32, i32, i32, vp, vp, vp, i32, i32, C.POINTER(C.c_float)]),
 }
 

@@ -480,6 +480,10 @@ struct slmm_chol {
   std::vector<cudaEvent_t> events;
   bool factored = false;
   bool profiling = false;
+  bool timeline = false;               // events of the two-stream schedules carry timestamps (eager issue, no graphs)
+  std::vector<cudaEvent_t> tl_events;  // timed twins of `events` + [0] = fork
+  std::vector<cudaEvent_t> tl_launch;  // one timed event after every kernel of the schedule
+  int tl_count = 0;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double prof_flops[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -553,13 +557,20 @@ static bool is_kernel(const Launch& L) { return L.kind != Launch::EV_RECORD && L
 // ONCE into a CUDA graph and replayed: a 12-column solve is a chain of ~1000 tiny launches whose cost was the
 // host's launch rate, not the kernels (SLMM_GRAPHS=0 falls back to launch-by-launch).
 static void issue_schedule(slmm_chol* h, const Schedule& sch, double* X, double* const* vec_arena,
-                           const int64_t* d_vptr, int nrhs, bool two, cudaStream_t one) {
+                           const int64_t* d_vptr, int nrhs, bool two, cudaStream_t one,
+                           std::vector<cudaEvent_t>* per_launch = nullptr) {
   const DevSym ds = h->devsym();
+  size_t nk = 0;
   for (const Launch& L : sch.launches) {
     cudaStream_t st = two ? (L.stream ? h->s_bulk : h->s_main) : one;
     if (L.kind == Launch::EV_RECORD) { if (two) CUDA_OK(cudaEventRecord(h->events[L.count], st)); continue; }
     if (L.kind == Launch::EV_WAIT) { if (two) CUDA_OK(cudaStreamWaitEvent(st, h->events[L.count], 0)); continue; }
     launch_one(h, sch, L, ds, X, vec_arena, d_vptr, nrhs, st);
+    if (per_launch) {                       // timeline mode: when did this launch finish (on its own stream)?
+      if (nk >= per_launch->size()) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); per_launch->push_back(e); }
+      CUDA_OK(cudaEventRecord((*per_launch)[nk], st));
+    }
+    nk++;
   }
 }
 
@@ -616,7 +627,34 @@ static void run_schedule(slmm_chol* h, Schedule& sch, double* X, double* const* 
       h->events.push_back(e);
     }
     const int gi = two ? 0 : 1;
-    if (graphs_enabled() && h->s_main != nullptr && !sch.graph_failed && sch.gexec[gi] == nullptr) {
+    if (h->timeline && two) {
+      // timeline mode: the same two-stream issue with TIMED events, so the host can read when each panel / bulk
+      // update finished relative to the fork (where is the critical path: the chain or the bulk stream?)
+      while ((int)h->tl_events.size() < sch.nevents + 2) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreate(&e));
+        h->tl_events.push_back(e);
+      }
+      std::vector<cudaEvent_t> saved = h->events;
+      for (int q = 0; q < sch.nevents; q++) h->events[q] = h->tl_events[q + 2];
+      CUDA_OK(cudaEventRecord(h->tl_events[0], 0));
+      CUDA_OK(cudaStreamWaitEvent(h->s_main, h->tl_events[0], 0));
+      CUDA_OK(cudaStreamWaitEvent(h->s_bulk, h->tl_events[0], 0));
+      issue_schedule(h, sch, X, vec_arena, d_vptr, nrhs, true, nullptr, &h->tl_launch);
+      CUDA_OK(cudaEventRecord(h->ev_join, h->s_bulk));
+      CUDA_OK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+      CUDA_OK(cudaEventRecord(h->tl_events[1], h->s_main));
+      CUDA_OK(cudaStreamWaitEvent(0, h->tl_events[1], 0));
+      CUDA_OK(cudaEventSynchronize(h->tl_events[1]));
+      h->events = saved;
+      h->tl_count = sch.nevents + 2;
+      g_launch_count += nk;
+      return;
+    }
+    // graphs for the single-stream lists only: replaying the look-ahead pair from a graph loses the stream priorities
+    // the chain relies on (measured: factorization 183 -> 190 ms at the 250K config)
+    const bool use_graph = graphs_enabled() && !two && h->s_main != nullptr && !sch.graph_failed;
+    if (use_graph && sch.gexec[gi] == nullptr) {
       try {
         sch.gexec[gi] = capture_schedule(h, sch, X, vec_arena, d_vptr, nrhs, two);
       } catch (const std::exception&) {
@@ -624,7 +662,7 @@ static void run_schedule(slmm_chol* h, Schedule& sch, double* X, double* const* 
         sch.gexec[gi] = nullptr;
       }
     }
-    cudaGraphExec_t exec = (graphs_enabled() && !sch.graph_failed) ? sch.gexec[gi] : nullptr;
+    cudaGraphExec_t exec = (use_graph && !sch.graph_failed) ? sch.gexec[gi] : nullptr;
     if (exec != nullptr && h->cur != nullptr) {
       CUDA_OK(cudaGraphLaunch(exec, h->cur));              // auxiliary section: the whole list on the auxiliary stream
     } else if (exec != nullptr || two) {
@@ -1250,6 +1288,8 @@ int slmm_chol_destroy(slmm_chol_t* h) {
   dev_free(h->Lx); dev_free(h->inv); dev_free(h->W); dev_free(h->wscratch); dev_free(h->d_wblocks); dev_free(h->arena[0]); dev_free(h->arena[1]);
   dev_free(h->d_info); dev_free(h->d_partial);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->tl_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->tl_launch) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->s_main) cudaStreamDestroy(h->s_main);
@@ -1521,6 +1561,53 @@ int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on) {
   for (int k = 0; k < 8; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
   h->prof_launch_ms.clear(); h->prof_launch_flops.clear(); h->prof_launch_kind.clear(); h->prof_launch_grid.clear();
   return SLMM_OK;
+}
+
+int slmm_chol_set_timeline(slmm_chol_t* h, int32_t on) {
+  if (!h) return SLMM_ERR_INVALID;
+  h->timeline = on != 0;
+  return SLMM_OK;
+}
+
+int slmm_chol_get_timeline(slmm_chol_t* h, int32_t max_n, int32_t* n_out, float* ms, int32_t* stream) {
+  SLMM_TRY
+  if (!h || !n_out) throw std::invalid_argument("null argument");
+  // entry q >= 2: event q-2 of the last two-stream schedule run in timeline mode (ms since the fork; stream that
+  // recorded it); entry 1: the join
+  const int n = h->tl_count;
+  *n_out = n;
+  if (ms) {
+    std::vector<int> rec_stream(std::max(0, n - 2), 0);
+    for (const Launch& L : h->fact.launches)
+      if (L.kind == Launch::EV_RECORD && L.count + 2 < n) rec_stream[L.count] = L.stream;
+    for (int q = 0; q < n && q < max_n; q++) {
+      float v = 0.f;
+      if (q > 0) CUDA_OK(cudaEventElapsedTime(&v, h->tl_events[0], h->tl_events[q]));
+      ms[q] = v;
+      if (stream) stream[q] = q >= 2 ? rec_stream[q - 2] : 0;
+    }
+  }
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
+int slmm_chol_get_launch_timeline(slmm_chol_t* h, int32_t max_n, int32_t* n_out, float* end_ms, int32_t* stream,
+                                  int32_t* kind, int32_t* grid, double* flops) {
+  SLMM_TRY
+  if (!h || !n_out) throw std::invalid_argument("null argument");
+  std::vector<const Launch*> ks;
+  for (const Launch& L : h->fact.launches) if (is_kernel(L)) ks.push_back(&L);
+  const int n = (int)std::min(ks.size(), h->tl_launch.size());
+  *n_out = n;
+  for (int q = 0; q < n && q < max_n; q++) {
+    if (end_ms) { float v = 0.f; CUDA_OK(cudaEventElapsedTime(&v, h->tl_events[0], h->tl_launch[q])); end_ms[q] = v; }
+    if (stream) stream[q] = ks[q]->stream;
+    if (kind) kind[q] = (int)ks[q]->kind;
+    if (grid) grid[q] = ks[q]->kind <= Launch::GEMM_SMALL ? ks[q]->grid : ks[q]->count;
+    if (flops) flops[q] = ks[q]->flops;
+  }
+  return SLMM_OK;
+  SLMM_CATCH
 }
 
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6) {

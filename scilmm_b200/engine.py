@@ -497,6 +497,29 @@ class CholEngine(object):
     def set_profiling(self, on):
         check(lib().slmm_chol_set_profiling(self._h, 1 if on else 0))
 
+    def timeline(self):
+        """Factorize once in timeline mode; returns (ms since the fork, recording stream) per schedule event."""
+        check(lib().slmm_chol_set_timeline(self._h, 1))
+        try:
+            self.factorize()
+        finally:
+            check(lib().slmm_chol_set_timeline(self._h, 0))
+        n = C.c_int32(0)
+        check(lib().slmm_chol_get_timeline(self._h, 0, C.byref(n), None, None))
+        ms, st = np.zeros(n.value, np.float32), np.zeros(n.value, np.int32)
+        check(lib().slmm_chol_get_timeline(self._h, n.value, C.byref(n), np_ptr(ms), np_ptr(st)))
+        return ms, st
+
+    def launch_timeline(self):
+        """Per kernel launch of the last timeline-mode factorization: (end ms, stream, kind, grid, flops)."""
+        n = C.c_int32(0)
+        check(lib().slmm_chol_get_launch_timeline(self._h, 0, C.byref(n), None, None, None, None, None))
+        end, fl = np.zeros(n.value, np.float32), np.zeros(n.value)
+        st, kind, grid = (np.zeros(n.value, np.int32) for _ in range(3))
+        check(lib().slmm_chol_get_launch_timeline(self._h, n.value, C.byref(n), np_ptr(end), np_ptr(st), np_ptr(kind),
+                                                  np_ptr(grid), np_ptr(fl)))
+        return end, st, kind, grid, fl
+
     def profile(self):
         """Per-kernel-kind device time (ms), issued flops and launch counts since set_profiling(True)."""
         ms, fl, n = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)

@@ -37,3 +37,7 @@ ses.eng.set_profiling(True); ses.eng.factorize(); report("factorize"); ses.eng.s
 B = torch.randn(nn, 128, dtype=torch.float64, device="cuda"); ses.eng.solve_(B.clone())
 ses.eng.set_profiling(True); ses.eng.solve_(B.clone()); report("solve 128 rhs"); ses.eng.set_profiling(False)
 ses.eng.lmul(B); ses.eng.set_profiling(True); ses.eng.lmul(B); report("lmul 128"); ses.eng.set_profiling(False)
+B12 = torch.randn(nn, 12, dtype=torch.float64, device="cuda"); ses.eng.solve_(B12.clone())
+ses.eng.set_profiling(True); ses.eng.solve_(B12.clone()); report("solve12 12 rhs"); ses.eng.set_profiling(False)
+ms, fl, kind, grid = ses.eng.launch_profile()
+print("  solve12 per-launch histogram (us):", np.percentile(ms * 1e3, [5, 25, 50, 75, 95]).round(1), "sum ms", ms.sum().round(2))

@@ -47,3 +47,20 @@ def test_simulator_and_household():
     keep, (Af, Hf) = P.drop_unrelated(A, H)
     assert Af.shape[0] == keep.sum() == Hf.shape[0]
     assert np.all(np.asarray(Af.sum(axis=1)).ravel() > 1)
+
+
+def test_npz_csr_io_matches_reference_format(tmp_path, golden_small):
+    """save_sparse_csr / load_sparse_csr (reference Matrices/SparseMatrixFunctions.py:5-13): same keys, exact round
+    trip, and a file written the way the reference writes it loads identically."""
+    import scilmm_b200
+    A = golden_small.csr("A")
+    scilmm_b200.save_sparse_csr(str(tmp_path / "IBD"), A)                 # np.savez appends .npz
+    z = np.load(tmp_path / "IBD.npz")
+    assert set(z.files) == {"data", "indices", "indptr", "shape"} and tuple(z["shape"]) == A.shape
+    B = scilmm_b200.load_sparse_csr(str(tmp_path / "IBD.npz"))
+    assert np.array_equal(B.indptr, A.indptr) and np.array_equal(B.indices, A.indices) and np.array_equal(B.data, A.data)
+    np.savez(tmp_path / "ref.npz", data=A.data, indices=A.indices, indptr=A.indptr, shape=A.shape)   # reference :6-7
+    Cm = scilmm_b200.load_sparse_csr(str(tmp_path / "ref.npz"))
+    assert (Cm != A).nnz == 0
+    E = scilmm_b200.pairwise_epistasis(A)
+    assert np.array_equal(sp.csr_matrix(E).data, golden_small.csr("E").data)
