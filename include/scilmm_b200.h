@@ -111,6 +111,21 @@ int slmm_device_arrays_equal_i32(const int32_t* d_a, const int32_t* d_b, int64_t
 /* *out = 1 when A_k equals its transpose bit for bit (device check, cached). */
 int slmm_matset_is_symmetric(slmm_matset_t* ms, int32_t k, int32_t* out);
 int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);
+
+/* Tiled variant of the quadratic-form / Gram pass for SYMMETRIC matrices (the production path of
+ * compute_gradients, SparseCholesky.py:62-74).  slmm_matset_build_tiles cuts the lower triangle of matrix k, in the
+ * fill-reducing order of a factor (d_perm[new] = old, d_iperm[old] = new: slmm_chol_device_perm), into tiles of 64
+ * permuted rows x 64 distinct columns - once per session, on the device; matrices sharing a pattern share the tiling.
+ * slmm_quadform_tiled then takes X = [XB | W] (C-ordered n x ncols, ncols <= 160; the first nb <= 16 columns are
+ * the narrow block [V^-1 C | V^-1 r]) in the ORIGINAL row order and returns
+ *   d_dots[g*ncols + c]  = x_c' A_ks[g] x_c            (np.sum(mats[i].dot(sim_vec) * sim_vec, axis=0), :65)
+ *   d_gram_half[g][nb][nb] with XB' A XB = half + half'   (:66 and :70)
+ * reading every gathered row of X once per tile from shared memory instead of once per entry through L2. */
+int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm, const int32_t* d_iperm);
+/* out4: tiles, entries on/below the diagonal, distinct (row block, column) pairs, CTAs of the pass */
+int slmm_matset_tile_stats(const slmm_matset_t* ms, int32_t k, int64_t* out4);
+int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols, int32_t nb,
+                        double* d_dots, double* d_gram_half);
 /* *out = 1 when the n x n CSR matrix in device memory equals its transpose bit for bit (pattern and values).
  * Guards the factor input: the engine keeps one triangle after the fill-reducing permutation, which is only
  * CHOLMOD's answer (it reads the lower triangle, SparseCholesky.py:23-26) when both triangles agree. */
@@ -135,6 +150,8 @@ int slmm_chol_destroy(slmm_chol_t* h);
 int slmm_chol_stats(const slmm_chol_t* h, int64_t* i_out, double* d_out);
 /* factor.P() (SparseCholesky.py:93): A[P][:,P] = L L' */
 int slmm_chol_perm(const slmm_chol_t* h, int32_t* h_perm);
+/* the same permutation and its inverse in device memory (owned by the handle) */
+int slmm_chol_device_perm(const slmm_chol_t* h, const int32_t** d_perm, const int32_t** d_iperm);
 
 /* Register the pattern of one input matrix (any CSR/CSC subset of the analysed pattern, host arrays) and get a
  * scatter map id; values with that pattern can then be streamed into the factor storage. */
@@ -196,6 +213,8 @@ int slmm_chol_copy_panels(slmm_chol_t* h, double* host_out);
 int slmm_launch_count(int64_t* out, int32_t reset);
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on);
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6);
+/* same for the first nkinds <= 12 kinds: ... 6 identity init, 7 split-K reduce, 10 / 11 narrow-RHS streaming kernels (flavour 1 / 2) */
+int slmm_chol_get_profile_ex(const slmm_chol_t* h, int32_t nkinds, double* ms, double* flops, int64_t* n);
 /* Timeline mode: the factorization's two-stream schedule is issued with TIMED events; after a factorization
  * slmm_chol_get_timeline returns, per event of the schedule, the ms since the fork and the stream that recorded it
  * (0 chain / 1 bulk; entry 0 = fork, entry 1 = join).  Shows whether the panel chain or the bulk updates are the

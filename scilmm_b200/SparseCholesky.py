@@ -13,6 +13,7 @@ which is the structural change against the reference (it re-analyses on every ca
 There is no CPU fallback: without the CUDA library these functions raise.
 """
 import hashlib
+import os
 import time
 
 import numpy as np
@@ -233,6 +234,16 @@ class RemlSession(object):
                 cache[ck] = self.eng.register_pattern_device(ptr_t, idx_t, self.matset.nnz[k], tri)
             self.map_ids.append(cache[ck])
         self.timings['maps_s'] = time.time() - t1
+        # tiled copies (fill-reducing order, 64 rows x 64 distinct columns) of the symmetric matrices for the
+        # quadratic-form / Gram pass of compute_gradients; tiny matrices (the identity) keep the row-per-warp kernel
+        t1 = time.time()
+        self.use_tiles = os.environ.get("SLMM_TILES", "1") != "0"
+        if self.use_tiles:
+            for ks in self._groups:
+                if all(self._sym[k] for k in ks) and self.matset.nnz[ks[0]] >= 8 * self.n:
+                    for k in ks:
+                        self.matset.build_tiles(k, self.eng)
+        self.timings['tiles_s'] = time.time() - t1
         self.C = _eng.to_device(np.asarray(covariates, dtype=np.float64), torch)
         self.y = _eng.to_device(np.asarray(y, dtype=np.float64), torch)
         self.C_host = np.asarray(covariates, dtype=np.float64)
@@ -349,8 +360,16 @@ class RemlSession(object):
         s_loc = W.shape[1]
         Bq = self._ViCy
         Bq[:, c] = Vir                                 # Viy was copied out above; the block becomes [V^-1 C | V^-1 r]
+        nbq = Bq.shape[1]
         for ks in self._groups:
-            if all(self._sym[k] for k in ks) and Bq.shape[1] <= 16 and s_loc <= 160:
+            if self.use_tiles and self.matset.has_tiles(ks) and nbq <= 16 and nbq + s_loc <= 160:
+                # tiled pass: X = [narrow block | probes], gathered rows staged in shared memory once per tile
+                dots, G = self.matset.quadform_tiled(ks, torch.cat([Bq, W], dim=1), nbq)
+                for g, k in enumerate(ks):
+                    comp1[k] = dots[g, nbq:].sum()
+                    comp2[k] = G[g][c, c]
+                    gram[k] = G[g][:c, :c]
+            elif all(self._sym[k] for k in ks) and Bq.shape[1] <= 16 and s_loc <= 160:
                 dots, G = self.matset.quadform_gram_multi(ks, W, Bq)
                 for g, k in enumerate(ks):
                     comp1[k] = dots[g].sum()

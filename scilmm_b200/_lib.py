@@ -36,6 +36,10 @@ SIGNATURES = {
     "slmm_matset_destroy": (C.c_int, [vp]),
     "slmm_matset_upload": (C.c_int, [vp, i32, vp, vp, vp]),
     "slmm_matset_bind_device": (C.c_int, [vp, i32, vp, vp, vp, i64, i32]),
+    "slmm_matset_build_tiles": (C.c_int, [vp, i32, vp, vp]),
+    "slmm_matset_tile_stats": (C.c_int, [vp, i32, vp]),
+    "slmm_quadform_tiled": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp]),
+    "slmm_chol_device_perm": (C.c_int, [vp, pp, pp]),
     "slmm_matset_set_row_range": (C.c_int, [vp, i32, i32]),
     "slmm_matset_symmetry_hash": (C.c_int, [vp, i32, vp]),
     "slmm_matset_set_symmetric": (C.c_int, [vp, i32, i32]),
@@ -79,6 +83,7 @@ SIGNATURES = {
     "slmm_chol_set_profiling": (C.c_int, [vp, i32]),
     "slmm_chol_set_timeline": (C.c_int, [vp, i32]),
     "slmm_chol_get_timeline": (C.c_int, [vp, i32, C.POINTER(i32), vp, vp]),
+    "slmm_chol_get_profile_ex": (C.c_int, [vp, i32, vp, vp, vp]),
     "slmm_chol_get_launch_timeline": (C.c_int, [vp, i32, C.POINTER(i32), vp, vp, vp, vp, vp]),
     "slmm_chol_get_profile": (C.c_int, [vp, vp, vp, vp]),
     "slmm_chol_get_launch_profile": (C.c_int, [vp, i64, C.POINTER(i64), vp, vp, vp, vp]),

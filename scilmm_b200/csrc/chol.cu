@@ -18,6 +18,7 @@
 #include "common.h"
 #include "dense_tiles.cuh"
 #include "potrf_block.cuh"
+#include "skinny_ops.cuh"
 #include "symbolic.h"
 
 namespace slmm {
@@ -249,7 +250,8 @@ __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __re
 // ---------------------------------------------------------------------------------------------------------
 struct Launch {
   // EV_RECORD / EV_WAIT carry no kernel: `count` is an event id, recorded on / awaited by the launch's stream
-  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG, INIT_W, REDUCE, EV_RECORD, EV_WAIT } kind;
+  enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG, INIT_W, REDUCE, EV_RECORD, EV_WAIT,
+              SKINNY_F1, SKINNY_F2 /* narrow-RHS streaming kernels; child_parity holds the row template MT */ } kind;
   int64_t off;      // offset into the matching op array
   int32_t count;    // ops / items
   int32_t grid;     // CTAs
@@ -276,7 +278,9 @@ struct Schedule {
   int32_t* d_tile_op = nullptr;
   int nevents = 0;                // events used by EV_RECORD / EV_WAIT
   int64_t ws_size = 0;            // doubles of split-K workspace (max over phases)
+  int64_t ws2_size = 0;           // second workspace: split-K of bulk-stream ops running beside the chain's
   double* d_ws = nullptr;
+  double* d_ws2 = nullptr;
   ReduceOp* d_reduce = nullptr;
   GemmOp* d_gemm = nullptr;
   PotrfOp* d_potrf = nullptr;
@@ -287,11 +291,17 @@ struct Schedule {
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   bool graph_failed = false;
   void upload() {
-    if (ws_size > 0) {              // patch workspace offsets into pointers
+    if (ws_size > 0 || ws2_size > 0) {              // patch workspace offsets into pointers
       d_ws = dev_alloc<double>(ws_size);
-      for (GemmOp& op : gemm)
+      d_ws2 = dev_alloc<double>(ws2_size);
+      for (GemmOp& op : gemm) {
         if (op.flags & GF_WS) { op.C = d_ws + (int64_t)(intptr_t)op.C; op.flags &= ~GF_WS; }
-      for (ReduceOp& r : reduce) r.ws = d_ws + (int64_t)(intptr_t)r.ws;
+        if (op.flags & GF_WS2) { op.C = d_ws2 + (int64_t)(intptr_t)op.C; op.flags &= ~GF_WS2; }
+      }
+      for (ReduceOp& r : reduce) {
+        r.ws = ((r.flags & GF_WS2) ? d_ws2 : d_ws) + (int64_t)(intptr_t)r.ws;
+        r.flags &= ~GF_WS2;
+      }
     }
     d_reduce = dev_upload(reduce.data(), reduce.size());
     d_gemm = dev_upload(gemm.data(), gemm.size());
@@ -302,19 +312,22 @@ struct Schedule {
   }
   void release() {
     for (int q = 0; q < 2; q++) if (gexec[q]) { cudaGraphExecDestroy(gexec[q]); gexec[q] = nullptr; }
-    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_reduce); dev_free(d_tile_op); dev_free(d_pull_entries);
+    dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_ws2); dev_free(d_reduce); dev_free(d_tile_op); dev_free(d_pull_entries);
+    d_ws2 = nullptr;
     d_tile_op = nullptr; d_pull_entries = nullptr;
     d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr; d_ws = nullptr; d_reduce = nullptr;
   }
   size_t device_bytes() const {
     return gemm.size() * sizeof(GemmOp) + potrf.size() * sizeof(PotrfOp) + pull.size() * sizeof(PullItem) +
-           reduce.size() * sizeof(ReduceOp) + (size_t)ws_size * 8 + tile_op.size() * 4 + pull_entries.size() * sizeof(PullEntry);
+           reduce.size() * sizeof(ReduceOp) + (size_t)(ws_size + ws2_size) * 8 + tile_op.size() * 4 + pull_entries.size() * sizeof(PullEntry);
   }
 };
 
 // collects the GEMM ops of one phase and splits them into the two tile configurations
 struct PhaseBuilder {
-  std::vector<GemmOp> big, small;
+  std::vector<GemmOp> big, small, sk1, sk2;   // sk1 / sk2: narrow-RHS streaming flavours (skinny_ops.cuh)
+  int skinny_mt = 0;                          // > 0: ops with M <= 16 take the streaming kernels (row template MT)
+  int ws_id = 0;                              // which split-K workspace this builder's partial products use
   std::vector<PotrfOp> potrf;
   std::vector<ReduceOp> reduces;
   int64_t ws_used = 0;
@@ -322,8 +335,58 @@ struct PhaseBuilder {
   void push(const GemmOp& op, bool small_tiles) {
     if (small_tiles) small.push_back(op); else big.push_back(op);
   }
+  // split op along K into S parts whose partial products land in the workspace, + the fixed-order reduction
+  template <typename Push>
+  void split_k(const GemmOp& op, int S, int kc, Push push) {
+    const int64_t mn = (int64_t)op.M * op.N;
+    ReduceOp r;
+    memset(&r, 0, sizeof(r));
+    r.C = op.C; r.c_si = op.c_si; r.c_sj = op.c_sj; r.M = op.M; r.N = op.N; r.S = S;
+    r.flags = (op.flags & (GF_ACCUM | GF_NEG)) | (ws_id ? GF_WS2 : 0);
+    r.ws = (const double*)(intptr_t)ws_used;
+    reduces.push_back(r);
+    for (int c = 0; c < S; c++) {
+      GemmOp part = op;
+      const int k0 = c * kc;
+      part.K = std::min(kc, op.K - k0);
+      if (op.a_kidx) part.a_kidx = op.a_kidx + k0; else part.A = op.A + (int64_t)k0 * op.a_sk;
+      part.B = op.B + (int64_t)k0 * op.b_sk;
+      part.C = (double*)(intptr_t)(ws_used + (int64_t)c * mn);
+      part.c_si = 1; part.c_sj = op.M;
+      part.flags = (ws_id ? GF_WS2 : GF_WS) | (op.flags & GF_TRIL_B);
+      part.pad = k0;                          // triangular B: first k of the part
+      push(part);
+    }
+    ws_used += (int64_t)S * mn;
+  }
+  bool add_skinny(const GemmOp& op) {
+    if (skinny_mt <= 0 || op.M > skinny_mt || op.a_si != 1 || op.c_si != 1 || (op.flags & (GF_LOWER | GF_BIGTILE))) return false;
+    const bool f1 = op.b_sj == 1 && op.a_kidx == nullptr;
+    if (!f1 && op.b_sk != 1) return false;
+    if (!f1 && (op.flags & GF_TRIL_B)) return false;
+    std::vector<GemmOp>& dst = f1 ? sk1 : sk2;
+    const int cols = f1 ? SK_F1_COLS : SK_F2_COLS, kmin = f1 ? 128 : 64;
+    const int64_t nj = (op.N + cols - 1) / cols;
+    // enough CTAs to keep the HBM pipe full (streaming kernels: ~4 resident CTAs per SM), K parts of >= kmin
+    int S = 1;
+    const int64_t target = 148 * 4;
+    const bool can_split = allow_split && op.C != op.A;
+    if (can_split && nj < target) S = (int)std::min<int64_t>((target + nj - 1) / nj, std::max(1, op.K / kmin));
+    if (!f1) S = std::max(S, (op.K + SK_F2_KMAX - 1) / SK_F2_KMAX);      // F2 stages its whole K range of A
+    if (S > 1 && !can_split) return false;
+    int kc = op.K;
+    if (S > 1) {
+      kc = (((op.K + S - 1) / S) + 15) / 16 * 16;
+      if (!f1) kc = std::min(kc, SK_F2_KMAX);
+      S = (op.K + kc - 1) / kc;
+    }
+    if (S <= 1) { GemmOp o = op; o.pad = 0; dst.push_back(o); }
+    else split_k(op, S, kc, [&](const GemmOp& part) { dst.push_back(part); });
+    return true;
+  }
   void add(GemmOp op) {
     if (op.M <= 0 || op.N <= 0 || op.K <= 0) return;
+    if (add_skinny(op)) return;
     // Tile configuration: 128 x 128 tiles for large outputs; outputs that would leave most of the 148 SMs idle
     // (the diagonal-block steps of the solves: nrhs x NBO with K = NBO) take 64 x 64 tiles and, when K allows,
     // split K across CTAs into workspace partials that splitk_reduce_kernel adds in fixed order.
@@ -341,25 +404,8 @@ struct PhaseBuilder {
       const int kc = S > 0 ? (((op.K + S - 1) / S) + 15) / 16 * 16 : op.K;
       S = (op.K + kc - 1) / kc;
       if (S >= 2) {
-        const int64_t mn = (int64_t)op.M * op.N;
-        ReduceOp r;
-        memset(&r, 0, sizeof(r));
-        r.C = op.C; r.c_si = op.c_si; r.c_sj = op.c_sj; r.M = op.M; r.N = op.N; r.S = S;
-        r.flags = op.flags & (GF_ACCUM | GF_NEG);
-        r.ws = (const double*)(intptr_t)ws_used;
-        reduces.push_back(r);
-        for (int c = 0; c < S; c++) {
-          GemmOp part = op;
-          const int k0 = c * kc;
-          part.K = std::min(kc, op.K - k0);
-          if (op.a_kidx) part.a_kidx = op.a_kidx + k0; else part.A = op.A + (int64_t)k0 * op.a_sk;
-          part.B = op.B + (int64_t)k0 * op.b_sk;
-          part.C = (double*)(intptr_t)(ws_used + (int64_t)c * mn);
-          part.c_si = 1; part.c_sj = op.M;
-          part.flags = GF_WS;
-          push(part, small_tiles);
-        }
-        ws_used += (int64_t)S * mn;
+        op.flags &= ~GF_TRIL_B;
+        split_k(op, S, kc, [&](GemmOp part) { part.pad = 0; part.flags = ws_id ? GF_WS2 : GF_WS; push(part, small_tiles); });
         return;
       }
     }
@@ -403,6 +449,31 @@ struct PhaseBuilder {
                               (int32_t)v.size(), (int32_t)tiles, 0, lf, tile_off});
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
+    for (int pass = 0; pass < 2; pass++) {      // narrow-RHS streaming flavours: one CTA per block of output columns
+      std::vector<GemmOp>& v = pass == 0 ? sk1 : sk2;
+      if (v.empty()) continue;
+      const int T = pass == 0 ? SK_F1_COLS : SK_F2_COLS;
+      int64_t tiles = 0;
+      double lf = 0;
+      for (GemmOp& op : v) {
+        op.tiles_m = 1;
+        op.tiles_n = (op.N + T - 1) / T;
+        op.tile_start = (int32_t)tiles;
+        tiles += op.tiles_n;
+        const double f = (op.flags & GF_TRIL_B) ? (double)op.M * op.N * op.K : 2.0 * op.M * op.N * op.K;
+        sch.flops += f;
+        lf += f;
+      }
+      if (tiles > 2000000000LL) throw std::runtime_error("too many tiles in one phase");
+      const int64_t tile_off = (int64_t)sch.tile_op.size();
+      sch.tile_op.resize(tile_off + tiles);
+      for (size_t q = 0; q < v.size(); q++)
+        std::fill(sch.tile_op.begin() + tile_off + v[q].tile_start,
+                  sch.tile_op.begin() + tile_off + v[q].tile_start + v[q].tiles_n, (int32_t)q);
+      sch.launches.push_back({pass == 0 ? Launch::SKINNY_F1 : Launch::SKINNY_F2, (int64_t)sch.gemm.size(),
+                              (int32_t)v.size(), (int32_t)tiles, skinny_mt, lf, tile_off});
+      sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
+    }
     if (!reduces.empty()) {
       int64_t blocks = 0;
       for (ReduceOp& r : reduces) {
@@ -411,13 +482,13 @@ struct PhaseBuilder {
       }
       sch.launches.push_back({Launch::REDUCE, (int64_t)sch.reduce.size(), (int32_t)reduces.size(), (int32_t)blocks, 0, 0.0});
       sch.reduce.insert(sch.reduce.end(), reduces.begin(), reduces.end());
-      sch.ws_size = std::max(sch.ws_size, ws_used);
+      if (ws_id) sch.ws2_size = std::max(sch.ws2_size, ws_used); else sch.ws_size = std::max(sch.ws_size, ws_used);
     }
     for (size_t q = first_launch; q < sch.launches.size(); q++) sch.launches[q].stream = stream;
-    big.clear(); small.clear(); potrf.clear(); reduces.clear();
+    big.clear(); small.clear(); sk1.clear(); sk2.clear(); potrf.clear(); reduces.clear();
     ws_used = 0;
   }
-  bool empty() const { return big.empty() && small.empty() && potrf.empty(); }
+  bool empty() const { return big.empty() && small.empty() && sk1.empty() && sk2.empty() && potrf.empty(); }
 };
 
 static GemmOp make_op(double* C, int64_t c_si, int64_t c_sj, const double* A, int64_t a_si, int64_t a_sk,
@@ -484,9 +555,9 @@ struct slmm_chol {
   std::vector<cudaEvent_t> tl_events;  // timed twins of `events` + [0] = fork
   std::vector<cudaEvent_t> tl_launch;  // one timed event after every kernel of the schedule
   int tl_count = 0;
-  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  double prof_flops[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_ms[16] = {};
+  double prof_flops[16] = {};
+  int64_t prof_n[16] = {};
   std::vector<float> prof_launch_ms;       // per launch of the last profiled schedule run
   std::vector<double> prof_launch_flops;
   std::vector<int32_t> prof_launch_kind, prof_launch_grid;
@@ -506,6 +577,8 @@ static void init_kernel_attributes() {
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
   CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF4_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 12 * 8));
+  CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 16 * 8));
   done = true;
 }
 
@@ -536,6 +609,25 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
     case Launch::REDUCE:
       splitk_reduce_kernel<<<L.grid, 256, 0, st>>>(sch.d_reduce + L.off, L.count);
       break;
+    case Launch::SKINNY_F1:
+    case Launch::SKINNY_F2: {
+      const GemmOp* ops = sch.d_gemm + L.off;
+      const int32_t* top = sch.d_tile_op + L.tile_off;
+      const bool f1 = L.kind == Launch::SKINNY_F1;
+#define SK_CASE(MT)                                                                                          \
+  if (f1) skinny_f1_kernel<MT><<<L.grid, SK_F1_COLS, 0, st>>>(ops, top);                                     \
+  else skinny_f2_kernel<MT><<<L.grid, 256, SK_F2_KMAX * MT * sizeof(double), st>>>(ops, top);
+      switch (L.child_parity) {
+        case 1: SK_CASE(1) break;
+        case 2: SK_CASE(2) break;
+        case 4: SK_CASE(4) break;
+        case 8: SK_CASE(8) break;
+        case 12: SK_CASE(12) break;
+        default: SK_CASE(16) break;
+      }
+#undef SK_CASE
+      break;
+    }
     case Launch::INIT_W:
       init_identity_kernel<<<L.count, 256, 0, st>>>(h->d_wblocks, h->W);
       break;
@@ -572,6 +664,12 @@ static void issue_schedule(slmm_chol* h, const Schedule& sch, double* X, double*
     }
     nk++;
   }
+}
+
+static bool skinny_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SLMM_SKINNY"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
 }
 
 static bool graphs_enabled() {
@@ -707,7 +805,7 @@ static void run_schedule(slmm_chol* h, Schedule& sch, double* X, double* const* 
       h->prof_launch_ms.push_back(ms);
       h->prof_launch_flops.push_back(ks[i]->flops);
       h->prof_launch_kind.push_back(k);
-      h->prof_launch_grid.push_back(ks[i]->kind <= Launch::GEMM_SMALL ? ks[i]->grid : ks[i]->count);
+      h->prof_launch_grid.push_back((ks[i]->kind <= Launch::GEMM_SMALL || ks[i]->kind >= Launch::SKINNY_F1) ? ks[i]->grid : ks[i]->count);
     }
     for (auto& e : ev) cudaEventDestroy(e);
   }
@@ -1036,7 +1134,12 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
   pl->bytes = ((size_t)2 * n * nrhs + asz[0] + asz[1]) * 8;
   const int64_t R = nrhs;
   PhaseBuilder pb, pb_rest;
-  pb_rest.allow_split = false;           // bulk-stream ops run beside the chain: one workspace, one user
+  // bulk-stream ops run beside the chain's: their split-K partials get a workspace of their own.  The bulk updates of
+  // consecutive diagonal blocks are serialised (same rows), and the late ones have far fewer tiles than SMs: without
+  // split-K each still costs one full-K tile latency (170 us at the 250K config whatever its size)
+  pb_rest.ws_id = 1;
+  if (nrhs <= 16 && skinny_enabled())    // narrow blocks: HBM-streaming kernels instead of DMMA tiles (skinny_ops.cuh)
+    pb.skinny_mt = nrhs <= 1 ? 1 : nrhs <= 2 ? 2 : nrhs <= 4 ? 4 : nrhs <= 8 ? 8 : nrhs <= 12 ? 12 : 16;
   const bool lookahead = nrhs >= 64;     // narrow solves are launch-latency chains: nothing to overlap with
   int last_bulk_ev = -1;
   // One phase: the chain's launches on the main stream; look-ahead remainders (if any) on the bulk stream, after
@@ -1329,6 +1432,13 @@ int slmm_chol_perm(const slmm_chol_t* h, int32_t* perm) {
   SLMM_CATCH
 }
 
+int slmm_chol_device_perm(const slmm_chol_t* h, const int32_t** d_perm, const int32_t** d_iperm) {
+  if (!h || !d_perm || !d_iperm) return SLMM_ERR_INVALID;
+  *d_perm = h->d_perm;
+  *d_iperm = h->d_iperm;
+  return SLMM_OK;
+}
+
 int slmm_chol_register_pattern_tri(slmm_chol_t* h, const int32_t* indptr, const int32_t* indices, int32_t tri,
                                    int32_t* map_id) {
   SLMM_TRY
@@ -1558,7 +1668,7 @@ int slmm_launch_count(int64_t* out, int32_t reset) {
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on) {
   if (!h) return SLMM_ERR_INVALID;
   h->profiling = on != 0;
-  for (int k = 0; k < 8; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
+  for (int k = 0; k < 16; k++) { h->prof_ms[k] = 0; h->prof_flops[k] = 0; h->prof_n[k] = 0; }
   h->prof_launch_ms.clear(); h->prof_launch_flops.clear(); h->prof_launch_kind.clear(); h->prof_launch_grid.clear();
   return SLMM_OK;
 }
@@ -1613,6 +1723,12 @@ int slmm_chol_get_launch_timeline(slmm_chol_t* h, int32_t max_n, int32_t* n_out,
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6) {
   if (!h || !ms6 || !flops6 || !n6) return SLMM_ERR_INVALID;
   for (int k = 0; k < 6; k++) { ms6[k] = h->prof_ms[k]; flops6[k] = h->prof_flops[k]; n6[k] = h->prof_n[k]; }
+  return SLMM_OK;
+}
+
+int slmm_chol_get_profile_ex(const slmm_chol_t* h, int32_t nkinds, double* ms, double* flops, int64_t* n) {
+  if (!h || !ms || !flops || !n || nkinds < 0 || nkinds > 16) return SLMM_ERR_INVALID;
+  for (int k = 0; k < nkinds; k++) { ms[k] = h->prof_ms[k]; flops[k] = h->prof_flops[k]; n[k] = h->prof_n[k]; }
   return SLMM_OK;
 }
 

@@ -19,7 +19,8 @@ constexpr int NBI = 64;   // diagonal block size (POTRF / inverse granularity)
 
 enum GemmFlags { GF_LOWER = 1, GF_ACCUM = 2, GF_NEG = 4, GF_WS = 8 /* C is an offset into the split-K workspace */,
                  GF_BIGTILE = 16 /* host-side only: keep the 128 x 128 tile configuration */,
-                 GF_TRIL_B = 32 /* B(j,k) = 0 for k > j (lower-triangular B): a tile stops at k = tn0 + TN */ };
+                 GF_TRIL_B = 32 /* B(j,k) = 0 for k > j (lower-triangular B): a tile stops at k = tn0 + TN */,
+                 GF_WS2 = 64 /* like GF_WS, in the second workspace (bulk-stream ops of the solves) */ };
 
 struct GemmOp {
   double* C;

@@ -11,24 +11,9 @@
 #include <vector>
 
 #include "common.h"
+#include "matset.h"
 
 namespace slmm {
-
-constexpr int MAXK = 8;
-
-struct CsrDev {
-  const int32_t* indptr = nullptr;
-  const int32_t* indices = nullptr;
-  const double* data = nullptr;
-  int64_t nnz = 0;
-  int pattern = -1;       // index of the first matrix with this pattern
-  bool owned_pattern = false, owned_data = false;
-  std::vector<int32_t> h_indptr;   // kept for pattern comparison (uploaded matrices only)
-  uint64_t idx_hash = 0;
-  int symmetric = -1;      // -1 unknown, 0 no, 1 yes (checked on the device on first use)
-  int32_t* rend = nullptr; // per row: one past the last entry with col <= row (pattern leaders only, built lazily)
-  int32_t* rend_base = nullptr;   // allocation behind rend (rend is shifted by -r0 for row-block shards)
-};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -291,7 +276,6 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 // One final reduction for ALL moments of an HE call: value j sums partial[off_j + b * stride_j] over its pass's
 // CTAs in fixed order and lands in dst[dst_j].  The descriptor table is cached on the device (it depends only on the
 // set of matrices), so a call issues its passes and this one kernel - no per-pass reductions, no small H2D copies.
-struct RedDesc { int64_t off; int32_t stride, nblocks, dst, pad; };
 __global__ void reduce_all_kernel(const double* __restrict__ partial, const RedDesc* __restrict__ desc,
                                   double* __restrict__ dst) {
   const RedDesc d = desc[blockIdx.x];
@@ -720,43 +704,6 @@ __global__ void __launch_bounds__(256) pattern_subset_kernel(const int32_t* __re
 
 using namespace slmm;
 
-struct slmm_matset {
-  int n = 0, K = 0;
-  int r0 = 0, r1 = 0;      // rows held by this set (a row-block shard of the HE path holds [r0, r1) only)
-  bool sharded() const { return r0 != 0 || r1 != n; }
-  std::vector<CsrDev> m;
-  std::map<std::pair<int, int>, int64_t*> cross_maps;   // (probe pattern, target pattern) -> position map (device)
-  double* d_partial = nullptr;
-  size_t partial_cap = 0;
-  double* d_y = nullptr;
-  double* d_out = nullptr;
-  int32_t* d_dst = nullptr;
-  // HE calls: one partial arena for all passes + the cached reduction table
-  double* he_arena = nullptr;
-  size_t he_used = 0;
-  static constexpr size_t HE_ARENA = (size_t)148 * 8 * 1024;
-  std::vector<slmm::RedDesc> he_desc, he_desc_cached;
-  slmm::RedDesc* d_he_desc = nullptr;
-  double* he_part(size_t count) {
-    if (!he_arena) he_arena = slmm::dev_alloc<double>(HE_ARENA);
-    if (he_used + count > HE_ARENA) throw std::runtime_error("HE partial arena exhausted");
-    double* p = he_arena + he_used;
-    he_used += count;
-    return p;
-  }
-  void he_add(const double* part, int nblocks, int nv, const int32_t* dst) {
-    for (int k = 0; k < nv; k++) he_desc.push_back({(int64_t)(part - he_arena) + k, nv, nblocks, dst[k], 0});
-  }
-  double* partial(size_t count) {
-    if (count > partial_cap) {
-      dev_free(d_partial);
-      d_partial = dev_alloc<double>(count);
-      partial_cap = count;
-    }
-    return d_partial;
-  }
-};
-
 namespace slmm {
 
 static uint64_t hash_bytes(const void* p, size_t nbytes) {
@@ -858,6 +805,7 @@ int slmm_matset_destroy(slmm_matset_t* ms) {
   dev_free(ms->d_partial); dev_free(ms->d_y); dev_free(ms->d_out); dev_free(ms->d_dst);
   dev_free(ms->he_arena); dev_free(ms->d_he_desc);
   for (auto& kv : ms->cross_maps) dev_free(kv.second);
+  for (auto& kv : ms->tiles) kv.second.release();
   delete ms;
   return SLMM_OK;
 }
@@ -871,6 +819,8 @@ int slmm_matset_upload(slmm_matset_t* ms, int32_t k, const int32_t* indptr, cons
   dev_free(c.rend_base);
   for (auto& kv : ms->cross_maps) dev_free(kv.second);
   ms->cross_maps.clear();
+  for (auto& kv : ms->tiles) kv.second.release();
+  ms->tiles.clear();
   c = CsrDev();
   if (ms->sharded()) throw std::invalid_argument("slmm_matset_upload takes whole matrices (row-block shards bind device arrays)");
   const int n = ms->n;
@@ -909,6 +859,8 @@ int slmm_matset_bind_device(slmm_matset_t* ms, int32_t k, const int32_t* d_indpt
   dev_free(c.rend_base);
   for (auto& kv : ms->cross_maps) dev_free(kv.second);
   ms->cross_maps.clear();
+  for (auto& kv : ms->tiles) kv.second.release();
+  ms->tiles.clear();
   c = CsrDev();
   // row-block shards: d_indptr has r1 - r0 + 1 entries counting from 0; the kernels index rows globally
   c.indptr = d_indptr - ms->r0; c.indices = d_indices; c.data = d_data; c.nnz = nnz;

@@ -342,6 +342,34 @@ class MatSet(object):
                                              dots.data_ptr(), half.data_ptr()))
         return dots, half + half.transpose(1, 2)
 
+    def build_tiles(self, k, chol_engine):
+        """Tile matrix k (symmetric) in the fill-reducing order of `chol_engine` for quadform_tiled."""
+        dp, di = chol_engine.device_perm()
+        check(lib().slmm_matset_build_tiles(self._h, int(k), dp, di))
+        self._tiled = getattr(self, "_tiled", set()) | {int(k)}
+
+    def tile_stats(self, k):
+        out = np.zeros(4, dtype=np.int64)
+        check(lib().slmm_matset_tile_stats(self._h, int(k), np_ptr(out)))
+        return dict(tiles=int(out[0]), entries=int(out[1]), distinct=int(out[2]), ctas=int(out[3]))
+
+    def has_tiles(self, ks):
+        t = getattr(self, "_tiled", set())
+        return all(int(k) in t for k in ks)
+
+    def quadform_tiled(self, ks, X, nb):
+        """One pass over the tiled symmetric matrices `ks` (one pattern): X = [XB (nb columns) | W], <= 160 columns.
+        Returns (dots[g, c] = X[:,c]' A X[:,c] for ALL columns, gram[g] = XB' A XB)."""
+        torch = _torch()
+        X2 = X.contiguous()
+        ncols = X2.shape[1]
+        ks_arr = np.asarray(ks, dtype=np.int32)
+        dots = torch.empty(len(ks), ncols, dtype=torch.float64, device="cuda")
+        half = torch.empty(len(ks), max(nb, 1), max(nb, 1), dtype=torch.float64, device="cuda")
+        check(lib().slmm_quadform_tiled(self._h, len(ks), np_ptr(ks_arr), X2.data_ptr(), int(ncols), int(nb),
+                                        dots.data_ptr(), half.data_ptr() if nb > 0 else None))
+        return dots, (half + half.transpose(1, 2)) if nb > 0 else None
+
     def is_symmetric(self, k):
         v = C.c_int32(0)
         check(lib().slmm_matset_is_symmetric(self._h, int(k), C.byref(v)))
@@ -421,6 +449,12 @@ class CholEngine(object):
             check(lib().slmm_chol_perm(self._h, np_ptr(p)))
             self._perm = p
         return self._perm
+
+    def device_perm(self):
+        """(d_perm, d_iperm) raw device pointers of the permutation (owned by the engine)."""
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib().slmm_chol_device_perm(self._h, C.byref(a), C.byref(b)))
+        return a, b
 
     def register_pattern(self, pattern, tri=0):
         """Scatter map of a host pattern.  tri: 0 = both triangles stored with equal values (verified by the
@@ -522,10 +556,12 @@ class CholEngine(object):
 
     def profile(self):
         """Per-kernel-kind device time (ms), issued flops and launch counts since set_profiling(True)."""
-        ms, fl, n = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)
-        check(lib().slmm_chol_get_profile(self._h, np_ptr(ms), np_ptr(fl), np_ptr(n)))
-        names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big"]
-        return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(6)}
+        ms, fl, n = np.zeros(12), np.zeros(12), np.zeros(12, dtype=np.int64)
+        check(lib().slmm_chol_get_profile_ex(self._h, 12, np_ptr(ms), np_ptr(fl), np_ptr(n)))
+        names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big", "init_w",
+                 "splitk_reduce", "_ev_record", "_ev_wait", "skinny_f1", "skinny_f2"]
+        return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(12)
+                if not names[k].startswith("_")}
 
     def launch_profile(self):
         """(ms, flops, kind, grid) arrays, one entry per launch of the profiled schedule runs."""

@@ -39,3 +39,15 @@ for ks in groups:
 B12 = torch.randn(ses.n, 12, dtype=torch.float64, device="cuda")
 T("solve_ 12", lambda: ses.eng.solve_(B12.clone()))
 T("solve_ 1", lambda: ses.eng.solve_(B12[:, 0].contiguous()))
+Xt = torch.cat([ses._ViCy, W], dim=1).contiguous()
+for ks in groups:
+    if ses.matset.has_tiles(ks):
+        print("tiles", ks, ses.matset.tile_stats(ks[0]), "setup", ses.timings)
+        T("quadform_tiled [B|W] %s" % ks, lambda: ses.matset.quadform_tiled(ks, Xt, ses._ViCy.shape[1]))
+        T("quadform_tiled W only %s" % ks, lambda: ses.matset.quadform_tiled(ks, W, 0))
+        X16 = Xt[:, :28].contiguous()
+        T("quadform_tiled 12+16 cols %s" % ks, lambda: ses.matset.quadform_tiled(ks, X16, 12))
+B16 = torch.randn(ses.n, 16, dtype=torch.float64, device="cuda")
+T("solve_ 16", lambda: ses.eng.solve_(B16.clone()))
+T("lmul 16", lambda: ses.eng.lmul(B16))
+T("hess", lambda: S._hess_device(ses, ses.eng), reps=1)

@@ -11,13 +11,13 @@ A, T, D, F = P.numerator(ped["rel"]); keep, (A,) = P.drop_unrelated(A); nn = A.s
 mats = [A, P.epistasis(A), sp.eye(nn).tocsr()]
 rng = np.random.default_rng(1); cov = np.hstack([rng.standard_normal((nn, 10)), np.ones((nn, 1))]); y = rng.standard_normal(nn)
 chol = S.SparseCholesky(rng="device"); ses = chol._session(mats, cov, y); sig = np.array([0.3, 0.15, 0.55])
-names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big"]
+names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big", "init_w", "reduce", "-", "-", "skinny_f1", "skinny_f2"]
 def report(tag):
     ms, fl, kind, grid = ses.eng.launch_profile()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.savez(os.path.join(ROOT, "gpurun_out", "launches_%s.npz" % tag.split()[0]), ms=ms, fl=fl, kind=kind, grid=grid)
     print("==", tag, "launches", ms.size, "total %.1f ms" % ms.sum())
-    for k in range(6):
+    for k in range(12):
         m = kind == k
         if m.sum() == 0: continue
         print("  %-10s n=%5d  %.1f ms  %.2f TFLOP/s" % (names[k], m.sum(), ms[m].sum(), fl[m].sum() / max(ms[m].sum(), 1e-9) / 1e9))
@@ -39,5 +39,3 @@ ses.eng.set_profiling(True); ses.eng.solve_(B.clone()); report("solve 128 rhs");
 ses.eng.lmul(B); ses.eng.set_profiling(True); ses.eng.lmul(B); report("lmul 128"); ses.eng.set_profiling(False)
 B12 = torch.randn(nn, 12, dtype=torch.float64, device="cuda"); ses.eng.solve_(B12.clone())
 ses.eng.set_profiling(True); ses.eng.solve_(B12.clone()); report("solve12 12 rhs"); ses.eng.set_profiling(False)
-ms, fl, kind, grid = ses.eng.launch_profile()
-print("  solve12 per-launch histogram (us):", np.percentile(ms * 1e3, [5, 25, 50, 75, 95]).round(1), "sum ms", ms.sum().round(2))

@@ -516,3 +516,89 @@ def test_device_ibd_builder_known_answers_and_errors():
     bad = sp.csr_matrix((np.ones(1, bool), ([0], [2])), shape=(4, 4))                    # parent after child
     with pytest.raises(SlmmError):
         ibd.numerator(bad)
+
+
+# ------------------------------------------------------------------------------------------ narrow-RHS kernels
+def test_narrow_rhs_streaming_kernels(slmm, eng):
+    """nrhs <= 16 takes the HBM-streaming kernels (csrc/skinny_ops.cuh): every row template (1, 2, 4, 8, 12, 16),
+    both flavours, split-K with the triangular bound (L*Z of a 2,500-column front), gathered rows with K > 512
+    (700 coupled rows below the dense front), against LAPACK and bit-reproducible."""
+    rng = np.random.default_rng(12)
+    nd, nt, nc = 2500, 900, 700
+    B = rng.standard_normal((nd, nd))
+    D = B @ B.T / nd + 2.0 * np.eye(nd)
+    T = sp.random(nt, nt, 0.02, random_state=2)
+    T = (T + T.T + 20 * sp.eye(nt)).toarray()
+    T[:nc, :nc] += 0.01
+    V = np.zeros((nd + nt, nd + nt))
+    C = 0.01 * rng.standard_normal((nd, nc))
+    V[:nd, :nd] = D
+    V[nd:, nd:] = T
+    V[:nd, nd:nd + nc] = C
+    V[nd:nd + nc, :nd] = C.T
+    Vs = sp.csc_matrix(V)
+    n = nd + nt
+    for ordering in ("natural", "nesdis"):
+        f = slmm.SparseCholesky(ordering_method=ordering)(Vs)
+        P = f.P()
+        Lref = la.cholesky(V[P][:, P], lower=True)
+        for k in (1, 2, 3, 5, 9, 12, 13, 16):
+            Bm = rng.standard_normal((n, k)) if k > 1 else rng.standard_normal(n)
+            X1, X2 = f(Bm), f(Bm)
+            assert np.array_equal(X1, X2)
+            assert rel_err(X1, np.linalg.solve(V, Bm)) < 1e-10, (ordering, k)
+            Z = rng.standard_normal((n, k))
+            got = f.lmul(eng.to_device(Z)).cpu().numpy()
+            want = (Lref @ Z)[np.argsort(P)]
+            assert rel_err(got, want) < 1e-11, (ordering, k)
+        # the two half sweeps on their own (mode 1: L^-1 P b, mode 2: P' L^-T)
+        Bm = rng.standard_normal((n, 6))
+        y = f._chol.solve_(eng.to_device(Bm), mode=1).cpu().numpy()
+        # mode 1 leaves the permuted forward solution scattered back through P
+        want = np.empty_like(Bm)
+        want[P] = la.solve_triangular(Lref, Bm[P], lower=True)
+        assert rel_err(y, want) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------ tiled quadratic forms
+@pytest.mark.parametrize("case", ["golden_c1mini", "golden_c1"])
+def test_tiled_quadforms_and_gram(case, request, slmm, eng):
+    """csrc/quadform_tiled.cu against scipy and against the row-per-warp kernels: column quadratic forms of a wide
+    block and the Gram matrix of the narrow block, K = 2 matrices on one pattern (A, A o A), ragged widths, a
+    permutation from the factor; bit-reproducible."""
+    import torch
+    g = request.getfixturevalue(case)
+    A, E_ = g.csr("A"), g.csr("E")
+    n = g.n
+    ms = eng.MatSet([A, E_])
+    f = slmm.SparseCholesky()(g.csc("V_k2"))
+    ms.build_tiles(0, f._chol)
+    ms.build_tiles(1, f._chol)
+    st = ms.tile_stats(0)
+    low = sp.tril(A).nnz
+    assert st["entries"] == low and 0 < st["distinct"] <= low and st["tiles"] >= (n + 63) // 64
+    rng = np.random.default_rng(8)
+    for ncols, nb in ((140, 12), (29, 12), (128, 0), (33, 3), (160, 16), (5, 5)):
+        X = rng.standard_normal((n, ncols))
+        Xd = eng.to_device(X)
+        for ks, mats in (([0, 1], [A, E_]), ([1], [E_])):
+            d1, G1 = ms.quadform_tiled(ks, Xd, nb)
+            d2, G2 = ms.quadform_tiled(ks, Xd, nb)
+            assert torch.equal(d1, d2) and (nb == 0 or torch.equal(G1, G2))
+            for gi, M in enumerate(mats):
+                want = np.sum(M.dot(X) * X, axis=0)
+                assert rel_err(d1[gi].cpu().numpy(), want) < 1e-12
+                if nb:
+                    wantG = X[:, :nb].T.dot(M.dot(X[:, :nb]))
+                    assert rel_err(G1[gi].cpu().numpy(), wantG) < 1e-12
+    # one REML evaluation with and without the tiled pass
+    mats, sig = g.mats("k4"), g["sig_k4"]
+    ys = g["y"] / g["y"].std()
+    Z = rng.standard_normal((n, 40))
+    out = []
+    for tiles in (True, False):
+        ses = slmm.SparseCholesky()._session(mats, g["cov"], ys)
+        assert ses.matset.has_tiles([0, 1]) and not ses.matset.has_tiles([3])
+        ses.use_tiles = tiles
+        out.append(ses.evaluate(sig, True, 40, Z=Z))
+    assert out[0][0] == out[1][0] and rel_err(out[0][1], out[1][1]) < 1e-11
