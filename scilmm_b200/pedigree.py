@@ -133,6 +133,120 @@ def simulate_pedigree(sample_size, sparse_factor, gen_exp=1.4, init_keep_rate=0.
     return dict(rel=rel, sex=sex, generation=generation, household=household, remove_frac=remove_frac)
 
 
+def simulate_tree(sample_size, sparse_factor, gen_exp, init_keep_rate, return_households=False):
+    """The reference's pedigree simulator, STREAM-IDENTICAL: same signature, same draws from the legacy global numpy
+    stream in the same order, same edge order, same Nelder-Mead search for the removal fraction - so
+    `np.random.seed(s); simulate_tree(...)` returns the relationship matrix the reference returns for that seed, bit for
+    bit (tests/test_generator_cpu.py checks it against matrices frozen from the unmodified reference).
+
+    reference: Simulation/Pedigree.py:93-124 (simulate_tree) with generation_size :17-21, households :35-54,
+    combine_ind_to_households :58-67, count_with_removed_edges / find_number_of_edges_to_remove :72-90.
+    What changes is the cost: the per-child Python list building becomes array code and the IBD-pattern count uses
+    float32 sparse products instead of boolean ones (same count).  Returns (rel, sex, generation) like the reference;
+    with return_households=True also the household id of every individual (-1 for founders)."""
+    from scipy.optimize import fmin
+    wanted = (sample_size ** 2) * sparse_factor
+    sizes = generation_sizes(sample_size, gen_exp)
+    bounds = np.concatenate(([0], np.cumsum(sizes)))
+    gens = [np.arange(bounds[i], bounds[i + 1]) for i in range(len(sizes))]
+    child, parent = [], []
+    household = np.full(sample_size, -1, dtype=np.int64)
+    hh_base = 0
+    for gi in range(1, len(gens)):
+        g, prev = gens[gi - 1], (None if gi == 1 else gens[gi - 2])
+        size = g.size
+        half = int(size / 2)
+        singles = np.random.choice(g, int(size * 0.32))                         # :38
+        k = int(size * 0.8 * 0.68)
+        s1 = np.random.choice(g[:half], k)                                      # :40
+        s2 = np.random.choice(g[half:], k)                                      # :41
+        p1 = [singles, s1]
+        p2 = [np.full(singles.size, -1, dtype=np.int64), s2]
+        if prev is not None:
+            phalf = int(prev.size / 2)
+            m = int(size * 0.2 * 0.68 * 0.5)
+            a1 = np.random.choice(g[:half], m)                                  # :49
+            b1 = np.random.choice(prev[phalf:], m)                              # :50
+            a2 = np.random.choice(prev[:phalf], m)                              # :51
+            b2 = np.random.choice(g[half:], m)                                  # :52
+            p1 += [a1, a2]
+            p2 += [b1, b2]
+        p1 = np.concatenate(p1).astype(np.int64)
+        p2 = np.concatenate(p2).astype(np.int64)
+        ok = p1 != p2                       # the reference's x != y filters (:42,:53); never true by construction
+        p1, p2 = p1[ok], p2[ok]
+        pick = np.random.choice(p1.size, gens[gi].size)                         # :62
+        household[gens[gi]] = hh_base + pick
+        hh_base += p1.size
+        c = gens[gi]
+        two = p2[pick] >= 0
+        # edges in the reference's order: children in order, each with its parents in household order
+        cnt = 1 + two.astype(np.int64)
+        cc = np.repeat(c, cnt)
+        pp = np.empty(cc.size, dtype=np.int64)
+        first = np.cumsum(cnt) - cnt
+        pp[first] = p1[pick]
+        pp[first[two] + 1] = p2[pick][two]
+        child.append(cc)
+        parent.append(pp)
+    edges = np.stack([np.concatenate(child), np.concatenate(parent)], axis=1)
+    total = edges.shape[0]
+    edges = edges[np.random.choice(total, int(total * init_keep_rate))]         # :67
+    rel = sp.csr_matrix((np.ones(edges.shape[0]), (edges[:, 0], edges[:, 1])), shape=(sample_size, sample_size),
+                        dtype=bool)
+    assert sp.triu(rel).nnz == 0
+    np.random.shuffle(edges)                                                    # :107
+
+    def removed(frac):
+        k = int(edges.shape[0] * frac)
+        m = rel.copy()
+        if k:
+            gone = sp.csr_matrix((np.ones(k, dtype=np.int8), (edges[:k, 0], edges[:k, 1])), shape=rel.shape)
+            m = (m.astype(np.int8) - m.astype(np.int8).multiply(gone.astype(bool))).tocsr()
+            m.eliminate_zeros()
+        return m.astype(bool).tocsr()
+
+    class _Found(Exception):
+        pass
+
+    def objective(part):                                                        # :72-81
+        diff = np.abs(ibd_pattern_count(removed(float(np.asarray(part).reshape(-1)[0]))) - wanted)
+        if diff < 0.1 * wanted:
+            raise _Found(float(np.asarray(part).reshape(-1)[0]))
+        return diff
+
+    res = None
+    try:
+        fmin(objective, 0.3, disp=False)                                        # :86 (returns without a hit -> None)
+    except _Found as ex:
+        res = ex.args[0]
+    if res is None:
+        raise Exception("Did not find a good enough tree")
+    rel = removed(res)
+    assert np.abs(ibd_pattern_count(rel) - wanted) < 0.1 * wanted
+    sex = np.zeros(sample_size)
+    gen_ind = np.zeros(sample_size)
+    for i, g in enumerate(gens):
+        sex[g[:int(g.size / 2)]] = 1
+        gen_ind[g] = i
+    if return_households:
+        return rel, sex, gen_ind, household
+    return rel, sex, gen_ind
+
+
+def quick_simulate_phenotype(ibd_L, covariate_matrix, sigma_g, fixed_effects, add_intercept=False):
+    """reference: Simulation/Phenotype.py:24-35, drawing from the legacy global numpy stream like the reference."""
+    n = ibd_L.shape[0]
+    sim = [ibd_L.dot(np.random.randn(n)), np.random.randn(n)]
+    sim = np.array(sim).T
+    sim = (sim - sim.mean(axis=0)) / sim.std(axis=0)
+    y = sim.dot(np.sqrt(np.array([sigma_g, 1 - sigma_g])))
+    if add_intercept:
+        covariate_matrix = np.hstack((covariate_matrix, np.ones((n, 1))))
+    y += covariate_matrix.dot(fixed_effects)
+    return (y - y.mean()) / y.std()
+
+
 def numerator(rel):
     """IBD / numerator relationship matrix A = T D T' with the inbreeding correction.
 

@@ -64,3 +64,22 @@ def test_npz_csr_io_matches_reference_format(tmp_path, golden_small):
     assert (Cm != A).nnz == 0
     E = scilmm_b200.pairwise_epistasis(A)
     assert np.array_equal(sp.csr_matrix(E).data, golden_small.csr("E").data)
+
+
+def test_simulate_tree_is_stream_identical_to_the_reference(golden_small, golden_c1mini, golden_c1):
+    """scilmm_b200.pedigree.simulate_tree draws from the legacy global numpy stream exactly like the reference's
+    Simulation/Pedigree.py:93-124: with the seed the golden files were frozen with, the relationship matrix, and the
+    phenotype of Simulation/Phenotype.py:24-35 drawn next, are the reference's bit for bit (config 1 included)."""
+    for g, n_sim, sf in ((golden_small, 400, 0.01), (golden_c1mini, 2500, 0.004), (golden_c1, 10000, 0.001)):
+        np.random.seed(g.seed)
+        rel, sex, gen, hh = P.simulate_tree(n_sim, sf, 1.4, 0.8, return_households=True)
+        rel = sp.csr_matrix(rel)
+        rel.sort_indices()
+        R = g.csr("rel")
+        assert np.array_equal(rel.indptr, R.indptr) and np.array_equal(rel.indices, R.indices)
+        assert sex.sum() > 0 and gen.max() >= 3 and hh.max() > 0 and np.all(hh[gen == 0] == -1)
+        A, T, D, F = P.numerator(rel)
+        np.random.seed(g.seed + 1)
+        cov_raw = np.random.randn(n_sim, 2)
+        y = P.quick_simulate_phenotype(T @ sp.diags(np.sqrt(D)), cov_raw, 0.4, np.arange(1, 3) * 0.1)
+        assert np.array_equal(y[g["keep"]], g["y"])
