@@ -213,7 +213,8 @@ int slmm_chol_copy_panels(slmm_chol_t* h, double* host_out);
 int slmm_launch_count(int64_t* out, int32_t reset);
 int slmm_chol_set_profiling(slmm_chol_t* h, int32_t on);
 int slmm_chol_get_profile(const slmm_chol_t* h, double* ms6, double* flops6, int64_t* n6);
-/* same for the first nkinds <= 12 kinds: ... 6 identity init, 7 split-K reduce, 10 / 11 narrow-RHS streaming kernels (flavour 1 / 2) */
+/* same for the first nkinds <= 16 kinds: ... 6 identity init, 7 split-K reduce, 10 / 11 narrow-RHS streaming kernels
+ * (flavour 1 / 2), 12 DMMA GEMM 128x128 tiles with TMA-staged operands */
 int slmm_chol_get_profile_ex(const slmm_chol_t* h, int32_t nkinds, double* ms, double* flops, int64_t* n);
 /* Timeline mode: the factorization's two-stream schedule is issued with TIMED events; after a factorization
  * slmm_chol_get_timeline returns, per event of the schedule, the ms since the fork and the stream that recorded it

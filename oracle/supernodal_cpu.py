@@ -61,6 +61,14 @@ class NotPositiveDefinite(np.linalg.LinAlgError):
     pass
 
 
+def _panel(Lx, a, s):
+    """(ms x ns) view of panel s: column-major with leading dimension a['sn_ld'][s] (the engine pads panels to an even
+    number of rows; an independent plan has ld = ms)."""
+    ns = a['sn_first'][s + 1] - a['sn_first'][s]
+    ms, ld, p0 = a['sn_nrow'][s], int(a['sn_ld'][s]), a['sn_lptr'][s]
+    return Lx[p0:p0 + ld * ns].reshape((ld, ns), order='F')[:ms]
+
+
 class SupernodalPlan(object):
     """Symbolic structures shared by factorizations with one pattern (host arrays from the engine's analysis)."""
 
@@ -114,7 +122,7 @@ class SupernodalCPUFactor(object):
                 ns = first[s + 1] - f
                 ms = nrow[s]
                 rs = ms - ns
-                panel = Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+                panel = _panel(Lx, a, s)
                 _set_blas_threads(ms * ns > SMALL_WORK)
                 Up = np.zeros((rs, rs), order='F') if rs else None
                 for c in plan.children[s]:
@@ -157,7 +165,7 @@ class SupernodalCPUFactor(object):
         for s in range(self.plan.sym.nsuper):
             ns = first[s + 1] - first[s]
             ms = nrow[s]
-            tot += np.sum(np.log(self.Lx[lptr[s]:lptr[s] + ms * ns:ms + 1][:ns]))
+            tot += np.sum(np.log(np.diagonal(_panel(self.Lx, a, s))[:ns]))
         return 2.0 * tot
 
     def L(self):
@@ -171,7 +179,7 @@ class SupernodalCPUFactor(object):
             ns = first[s + 1] - f
             ms = nrow[s]
             rows = a['rows'][rowptr[s]:rowptr[s + 1]]
-            panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+            panel = _panel(self.Lx, a, s)
             for c in range(ns):
                 ri.append(rows[c:])
                 vv.append(panel[c:, c])
@@ -194,7 +202,7 @@ class SupernodalCPUFactor(object):
                 f = first[s]
                 ns = first[s + 1] - f
                 ms = nrow[s]
-                panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+                panel = _panel(self.Lx, a, s)
                 _set_blas_threads(ms * ns > SMALL_WORK)
                 xt = XT[:, f:f + ns]
                 if ns == 1:
@@ -210,7 +218,7 @@ class SupernodalCPUFactor(object):
                 f = first[s]
                 ns = first[s + 1] - f
                 ms = nrow[s]
-                panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+                panel = _panel(self.Lx, a, s)
                 _set_blas_threads(ms * ns > SMALL_WORK)
                 xt = XT[:, f:f + ns]
                 if ms > ns:
@@ -246,7 +254,7 @@ class SupernodalCPUFactor(object):
             ns = first[s + 1] - f
             ms = nrow[s]
             rows = a['rows'][rowptr[s]:rowptr[s + 1]]
-            panel = self.Lx[lptr[s]:lptr[s + 1]].reshape((ms, ns), order='F')
+            panel = _panel(self.Lx, a, s)
             _set_blas_threads(ms * ns > SMALL_WORK)
             out[rows] += panel @ Z[f:f + ns]
         _set_blas_threads(True)

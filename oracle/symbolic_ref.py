@@ -106,7 +106,8 @@ class IndependentPlan(object):
         order = np.argsort(depth, kind="stable").astype(np.int32)
         level_ptr = np.concatenate(([0], np.cumsum(np.bincount(depth, minlength=nlevels)))).astype(np.int32)
         self.a = dict(perm=perm, parent=parent, colcount=cc, sn_first=sn_first, sn_nrow=sn_nrow, sn_parent=sn_parent,
-                      sn_rowptr=sn_rowptr, sn_lptr=sn_lptr, rows=rows, rel=rel, level_ptr=level_ptr, level_sn=order)
+                      sn_rowptr=sn_rowptr, sn_lptr=sn_lptr, rows=rows, rel=rel, level_ptr=level_ptr, level_sn=order,
+                      sn_ld=sn_nrow.astype(np.int64))
         self._iperm, self._col2sn = iperm, col2sn
         sym = _Sym()
         sym.n, sym.nsuper, sym.nlevels = n, nsuper, nlevels

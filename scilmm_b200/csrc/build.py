@@ -11,7 +11,7 @@ NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 METIS = os.path.join(CUDA_HOME, "lib64", "libmetis_static.a")
 SOURCES_CU = ["chol.cu", "sparse_ops.cu", "ibd.cu", "quadform_tiled.cu"]
 SOURCES_CPP = ["symbolic.cpp"]
-HEADERS = ["common.h", "dense_tiles.cuh", "potrf_block.cuh", "symbolic.h", "skinny_ops.cuh", "matset.h"]
+HEADERS = ["common.h", "dense_tiles.cuh", "potrf_block.cuh", "symbolic.h", "skinny_ops.cuh", "matset.h", "dense_tiles_tma.cuh"]
 
 
 def _stale():

@@ -2,7 +2,8 @@
 // Host code here only builds launch schedules (once per pattern / per RHS width) and walks them.
 //
 // Data layout in HBM
-//   panels   : for supernode s the ms x ns column-major trapezoid (ld = ms) at sn_lptr[s]; strict upper part of
+//   panels   : for supernode s the ms x ns column-major trapezoid (ld = ms rounded up to even, symbolic.h panel_ld)
+//              at sn_lptr[s]; strict upper part of
 //              the diagonal block stays zero.
 //   inverses : one 64 x 64 column-major slot per diagonal block (TRSM and the triangular solves become GEMMs).
 //   arena[2] : update (Schur complement) matrices rs x rs, ping-pong by depth parity, so a child's update lives
@@ -17,6 +18,7 @@
 
 #include "common.h"
 #include "dense_tiles.cuh"
+#include "dense_tiles_tma.cuh"
 #include "potrf_block.cuh"
 #include "skinny_ops.cuh"
 #include "symbolic.h"
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(TPI < 128 ? 128 : TPI) extend_add_kernel(const
     for (int tt = en.ta; tt < en.tb; tt++) {
       const int pc = relc[tt];
       const double* __restrict__ src = Uc + (int64_t)tt * rsc;
-      double* dst = pc < nsp ? panel + (int64_t)pc * msp : Up + (int64_t)(pc - nsp) * rsp - nsp;
+      double* dst = pc < nsp ? panel + (int64_t)pc * ((msp + 1) & ~1) : Up + (int64_t)(pc - nsp) * rsp - nsp;
       int u = tt + lane;
       for (; u + 3 * TPI < rsc; u += 4 * TPI) {
         const int r0 = relc[u], r1 = relc[u + TPI], r2 = relc[u + 2 * TPI], r3 = relc[u + 3 * TPI];
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256) entry_map_kernel(const int32_t* __restric
         const int ms = S.sn_nrow[s];
         const int32_t* rows = S.rows + S.sn_rowptr[s];
         const int pos = lower_bound_dev(rows, ms, ir);
-        if (pos < ms && rows[pos] == ir) out = S.sn_lptr[s] + (int64_t)(ic - S.sn_first[s]) * ms + pos;
+        if (pos < ms && rows[pos] == ir) out = S.sn_lptr[s] + (int64_t)(ic - S.sn_first[s]) * ((ms + 1) & ~1) + pos;
         else *bad = 1;
       }
       target[p] = out;
@@ -236,7 +238,7 @@ __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __re
   double acc = 0.0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int s = col2sn[j], c = j - sn_first[s];
-    acc += log(Lx[sn_lptr[s] + (int64_t)c * sn_nrow[s] + c]);
+    acc += log(Lx[sn_lptr[s] + (int64_t)c * ((sn_nrow[s] + 1) & ~1) + c]);
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -251,7 +253,8 @@ __global__ void logdet_kernel(const double* __restrict__ Lx, const int32_t* __re
 struct Launch {
   // EV_RECORD / EV_WAIT carry no kernel: `count` is an event id, recorded on / awaited by the launch's stream
   enum Kind { POTRF, GEMM_BIG, GEMM_SMALL, PULL_MAT, PULL_VEC, PULL_MAT_BIG, INIT_W, REDUCE, EV_RECORD, EV_WAIT,
-              SKINNY_F1, SKINNY_F2 /* narrow-RHS streaming kernels; child_parity holds the row template MT */ } kind;
+              SKINNY_F1, SKINNY_F2 /* narrow-RHS streaming kernels; child_parity holds the row template MT */,
+              GEMM_TMA /* 128 x 128 DMMA tiles with TMA-staged operands (dense_tiles_tma.cuh); aux_off = first tensor map */ } kind;
   int64_t off;      // offset into the matching op array
   int32_t count;    // ops / items
   int32_t grid;     // CTAs
@@ -259,7 +262,40 @@ struct Launch {
   double flops;     // dense flops issued by this launch (0 for pulls)
   int64_t tile_off; // GEMM launches: offset of this launch's tile -> op table
   int32_t stream;   // 0: main (high priority) stream   1: bulk stream (look-ahead trailing updates)
+  int64_t aux_off = 0;
 };
+
+static bool tma_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SLMM_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda: it must load
+// on machines without a driver for the host-only analysis).  2-D FP64 tensor: dim 0 = rows (contiguous), dim 1 = k
+// with a stride of `ld` elements; boxes of 16 x 16 elements, 128-byte swizzle.
+static CUtensorMap encode_tmap(const double* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available");
+    fn = (EncodeFn)p;
+  }
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {rows, cols};
+  const cuuint64_t gstride[1] = {ld * sizeof(double)};
+  const cuuint32_t box[2] = {16, (cuuint32_t)TMA_KS};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+  return m;
+}
 
 constexpr int BIG_STAGES = 4, SMALL_STAGES = 4;
 constexpr int BIG_SMEM = BIG_STAGES * 16 * (128 + 4) * 2 * 8 + 2 * BIG_STAGES * 8;
@@ -274,6 +310,8 @@ struct Schedule {
   std::vector<PullEntry> pull_entries;
   PullEntry* d_pull_entries = nullptr;
   std::vector<ReduceOp> reduce;
+  std::vector<CUtensorMap> tmaps; // two per GEMM_TMA op (A, B), in op order
+  CUtensorMap* d_tmaps = nullptr;
   std::vector<int32_t> tile_op;   // per GEMM launch: op index (relative to the launch's first op) of every tile
   int32_t* d_tile_op = nullptr;
   int nevents = 0;                // events used by EV_RECORD / EV_WAIT
@@ -308,12 +346,14 @@ struct Schedule {
     d_potrf = dev_upload(potrf.data(), potrf.size());
     d_pull = dev_upload(pull.data(), pull.size());
     d_tile_op = dev_upload(tile_op.data(), tile_op.size());
+    d_tmaps = dev_upload(tmaps.data(), tmaps.size());
     d_pull_entries = dev_upload(pull_entries.data(), pull_entries.size());
   }
   void release() {
     for (int q = 0; q < 2; q++) if (gexec[q]) { cudaGraphExecDestroy(gexec[q]); gexec[q] = nullptr; }
     dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_ws2); dev_free(d_reduce); dev_free(d_tile_op); dev_free(d_pull_entries);
     d_ws2 = nullptr;
+    dev_free(d_tmaps); d_tmaps = nullptr;
     d_tile_op = nullptr; d_pull_entries = nullptr;
     d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr; d_ws = nullptr; d_reduce = nullptr;
   }
@@ -326,14 +366,21 @@ struct Schedule {
 // collects the GEMM ops of one phase and splits them into the two tile configurations
 struct PhaseBuilder {
   std::vector<GemmOp> big, small, sk1, sk2;   // sk1 / sk2: narrow-RHS streaming flavours (skinny_ops.cuh)
+  std::vector<GemmOp> tma;                    // big-tile ops whose operands a tensor map can describe (dense_tiles_tma.cuh)
   int skinny_mt = 0;                          // > 0: ops with M <= 16 take the streaming kernels (row template MT)
   int ws_id = 0;                              // which split-K workspace this builder's partial products use
   std::vector<PotrfOp> potrf;
   std::vector<ReduceOp> reduces;
   int64_t ws_used = 0;
   bool allow_split = true;    // builders whose launches run beside another builder's must not share the split-K workspace
+  static bool tma_ok(const GemmOp& op) {
+    return tma_enabled() && op.a_si == 1 && op.b_sj == 1 && op.a_kidx == nullptr && !(op.flags & GF_TRIL_B) &&
+           (op.a_sk % 2) == 0 && (op.b_sk % 2) == 0 && op.a_sk > 0 && op.b_sk > 0 && op.K >= 64;
+  }
   void push(const GemmOp& op, bool small_tiles) {
-    if (small_tiles) small.push_back(op); else big.push_back(op);
+    if (small_tiles) small.push_back(op);
+    else if (tma_ok(op)) tma.push_back(op);
+    else big.push_back(op);
   }
   // split op along K into S parts whose partial products land in the workspace, + the fixed-order reduction
   template <typename Push>
@@ -419,10 +466,10 @@ struct PhaseBuilder {
       sch.launches.push_back({Launch::POTRF, (int64_t)sch.potrf.size(), (int32_t)potrf.size(), (int32_t)potrf.size(), 0, pf});
       sch.potrf.insert(sch.potrf.end(), potrf.begin(), potrf.end());
     }
-    for (int pass = 0; pass < 2; pass++) {
-      std::vector<GemmOp>& v = pass == 0 ? big : small;
+    for (int pass = 0; pass < 3; pass++) {
+      std::vector<GemmOp>& v = pass == 0 ? tma : pass == 1 ? big : small;
       if (v.empty()) continue;
-      const int T = pass == 0 ? 128 : 64;
+      const int T = pass == 2 ? 64 : 128;
       int64_t tiles = 0;
       double lf = 0;
       for (GemmOp& op : v) {
@@ -445,8 +492,20 @@ struct PhaseBuilder {
       for (size_t q = 0; q < v.size(); q++)
         std::fill(sch.tile_op.begin() + tile_off + v[q].tile_start,
                   sch.tile_op.begin() + tile_off + v[q].tile_start + (int64_t)v[q].tiles_m * v[q].tiles_n, (int32_t)q);
-      sch.launches.push_back({pass == 0 ? Launch::GEMM_BIG : Launch::GEMM_SMALL, (int64_t)sch.gemm.size(),
-                              (int32_t)v.size(), (int32_t)tiles, 0, lf, tile_off});
+      if (pass == 0) {
+        // tensor maps of the two operands: base rounded down to 16 bytes (op.pad bit 0 / 1 = the operand starts one
+        // element after its map's base), extents = the op's own M / N x K so that ragged edges are zero-filled
+        for (GemmOp& op : v) {
+          const int sa = (int)(((uintptr_t)op.A >> 3) & 1), sb = (int)(((uintptr_t)op.B >> 3) & 1);
+          op.pad = sa | (sb << 1);
+          sch.tmaps.push_back(encode_tmap(op.A - sa, (uint64_t)op.M + sa, (uint64_t)op.K, (uint64_t)op.a_sk));
+          sch.tmaps.push_back(encode_tmap(op.B - sb, (uint64_t)op.N + sb, (uint64_t)op.K, (uint64_t)op.b_sk));
+        }
+      }
+      Launch L{pass == 0 ? Launch::GEMM_TMA : pass == 1 ? Launch::GEMM_BIG : Launch::GEMM_SMALL, (int64_t)sch.gemm.size(),
+               (int32_t)v.size(), (int32_t)tiles, 0, lf, tile_off};
+      if (pass == 0) L.aux_off = (int64_t)sch.tmaps.size() - 2 * (int64_t)v.size();
+      sch.launches.push_back(L);
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
     for (int pass = 0; pass < 2; pass++) {      // narrow-RHS streaming flavours: one CTA per block of output columns
@@ -485,10 +544,10 @@ struct PhaseBuilder {
       if (ws_id) sch.ws2_size = std::max(sch.ws2_size, ws_used); else sch.ws_size = std::max(sch.ws_size, ws_used);
     }
     for (size_t q = first_launch; q < sch.launches.size(); q++) sch.launches[q].stream = stream;
-    big.clear(); small.clear(); sk1.clear(); sk2.clear(); potrf.clear(); reduces.clear();
+    big.clear(); small.clear(); tma.clear(); sk1.clear(); sk2.clear(); potrf.clear(); reduces.clear();
     ws_used = 0;
   }
-  bool empty() const { return big.empty() && small.empty() && sk1.empty() && sk2.empty() && potrf.empty(); }
+  bool empty() const { return big.empty() && small.empty() && tma.empty() && sk1.empty() && sk2.empty() && potrf.empty(); }
 };
 
 static GemmOp make_op(double* C, int64_t c_si, int64_t c_sj, const double* A, int64_t a_si, int64_t a_sk,
@@ -577,6 +636,7 @@ static void init_kernel_attributes() {
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM));
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
   CUDA_OK(cudaFuncSetAttribute(potrf_inv_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF4_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(gemm_tiles_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
   CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 12 * 8));
   CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 16 * 8));
   done = true;
@@ -590,6 +650,9 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       break;
     case Launch::GEMM_BIG:
       gemm_tiles_kernel<128, 128, 2, 4, BIG_STAGES><<<L.grid, BIG_THREADS, BIG_SMEM, st>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
+      break;
+    case Launch::GEMM_TMA:
+      gemm_tiles_tma_kernel<<<L.grid, TMA_THREADS, TMA_SMEM, st>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off, sch.d_tmaps + L.aux_off);
       break;
     case Launch::GEMM_SMALL:
       gemm_tiles_kernel<64, 64, 2, 2, SMALL_STAGES><<<L.grid, SMALL_THREADS, SMALL_SMEM, st>>>(sch.d_gemm + L.off, sch.d_tile_op + L.tile_off);
@@ -953,7 +1016,7 @@ static void build_factor_schedule(slmm_chol* h) {
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
         const bool wide = ns > NBO;
         double* P = h->Lx + S.sn_lptr[s];
-        const int64_t ld = ms;
+        const int64_t ld = panel_ld(ms);
         if (st.kind == FStep::POTRF || st.kind == FStep::TRSM || st.kind == FStep::UPD) {
           const int ib = st.a, c0 = ib * NBI, c1 = std::min(ns, c0 + NBI), nb = c1 - c0;
           const int ob = c0 / NBO, ob0 = ob * NBO, ob_end = std::min(ns, ob0 + NBO);
@@ -1077,7 +1140,7 @@ static void build_factor_schedule(slmm_chol* h) {
           const int ns = S.sn_first[s2 + 1] - S.sn_first[s2];
           if (ns <= NBI || ns > NBO) continue;
           double* P = h->Lx + S.sn_lptr[s2];
-          const int64_t ldp = S.sn_nrow[s2];
+          const int64_t ldp = panel_ld(S.sn_nrow[s2]);
           for (int ob = 0; ob < num_outer(ns); ob++) {
             const OuterBlock b = outer_block(h, s2, ob);
             if (b.nbo <= NBI || t * NBI >= b.nbo) continue;
@@ -1178,7 +1241,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
         const int nob = num_outer(ns);
         double* P = h->Lx + S.sn_lptr[s];
-        const int64_t ld = ms;
+        const int64_t ld = panel_ld(ms);
         double* Xs = pl->X + (int64_t)f * R;
         double* Ys = pl->X2 + (int64_t)f * R;
         if (ph == 2 * nob) {                       // contribution block  u = -L21 y   (rs x nrhs)
@@ -1225,7 +1288,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
         const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
         const int nob = num_outer(ns);
         double* P = h->Lx + S.sn_lptr[s];
-        const int64_t ld = ms;
+        const int64_t ld = panel_ld(ms);
         double* Xs = pl->X + (int64_t)f * R;
         double* Ys = pl->X2 + (int64_t)f * R;
         if (ph == 0) {                             // y_top -= L21' x[rows below]   (gathered rows of X)
@@ -1262,7 +1325,7 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
       const int s = S.level_sn[q];
       const int f = S.sn_first[s], ns = S.sn_first[s + 1] - f, ms = S.sn_nrow[s], rs = ms - ns;
       double* P = h->Lx + S.sn_lptr[s];
-      const int64_t ld = ms;
+      const int64_t ld = panel_ld(ms);
       // out_top = L11 z_top (upper part of the diagonal block is stored as zeros)
       pb.add(make_op(pl->X2 + (int64_t)f * R, 1, R, pl->X + (int64_t)f * R, 1, R, P, 1, ld, nrhs, ns, ns, GF_TRIL_B));
       if (rs > 0)
@@ -1617,7 +1680,7 @@ int slmm_chol_export_L(slmm_chol_t* h, int64_t* colptr, int32_t* rowidx, double*
     const double* P = Lh.data() + S.sn_lptr[s];
     for (int c = 0; c < ns; c++) {
       colptr[f + c] = q;
-      for (int r = c; r < ms; r++) { rowidx[q] = rows[r]; values[q] = P[r + (int64_t)c * ms]; q++; }
+      for (int r = c; r < ms; r++) { rowidx[q] = rows[r]; values[q] = P[r + (int64_t)c * panel_ld(ms)]; q++; }
     }
   }
   colptr[S.n] = q;
@@ -1713,7 +1776,7 @@ int slmm_chol_get_launch_timeline(slmm_chol_t* h, int32_t max_n, int32_t* n_out,
     if (end_ms) { float v = 0.f; CUDA_OK(cudaEventElapsedTime(&v, h->tl_events[0], h->tl_launch[q])); end_ms[q] = v; }
     if (stream) stream[q] = ks[q]->stream;
     if (kind) kind[q] = (int)ks[q]->kind;
-    if (grid) grid[q] = ks[q]->kind <= Launch::GEMM_SMALL ? ks[q]->grid : ks[q]->count;
+    if (grid) grid[q] = (ks[q]->kind <= Launch::GEMM_SMALL || ks[q]->kind >= Launch::SKINNY_F1) ? ks[q]->grid : ks[q]->count;
     if (flops) flops[q] = ks[q]->flops;
   }
   return SLMM_OK;

@@ -454,7 +454,7 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
     int64_t q = S.sn_rowptr[s];
     for (int j = 0; j < ns; j++) S.rows[q++] = f + j;
     for (int i : below[s]) S.rows[q++] = i;
-    S.sn_lptr[s + 1] = S.sn_lptr[s] + (int64_t)S.sn_nrow[s] * ns;
+    S.sn_lptr[s + 1] = S.sn_lptr[s] + panel_ld(S.sn_nrow[s]) * ns;
     S.max_front_rows = std::max(S.max_front_rows, S.sn_nrow[s]);
     S.max_super_cols = std::max(S.max_super_cols, ns);
   }
@@ -518,7 +518,7 @@ void entry_map(const Symbolic& S, const int32_t* ap, const int32_t* ai, int64_t*
       const int32_t* re = S.rows.data() + S.sn_rowptr[s + 1];
       const int32_t* it = std::lower_bound(rb, re, ir);
       if (it == re || *it != ir) throw std::runtime_error("matrix entry outside the analysed pattern");
-      target[p] = S.sn_lptr[s] + (int64_t)(ic - f) * S.sn_nrow[s] + (it - rb);
+      target[p] = S.sn_lptr[s] + (int64_t)(ic - f) * panel_ld(S.sn_nrow[s]) + (it - rb);
     }
   }
 }

@@ -9,6 +9,10 @@
 
 namespace slmm {
 
+// Leading dimension of a panel with `nrow` rows: rounded up to even, so that every panel column starts on a 16-byte
+// boundary - the alignment bulk tensor copies (TMA) need for the global strides of a tensor map.
+inline int64_t panel_ld(int64_t nrow) { return (nrow + 1) & ~(int64_t)1; }
+
 enum Ordering { ORD_NATURAL = 0, ORD_GIVEN = 1, ORD_METIS = 2, ORD_MINDEG = 3 };
 
 struct SymbolicOptions {
@@ -35,7 +39,7 @@ struct Symbolic {
   std::vector<int32_t> sn_parent;   // supernodal etree (-1 root)
   std::vector<int32_t> sn_depth;    // 0 at roots
   std::vector<int64_t> sn_rowptr;   // [nsuper+1] into rows[]
-  std::vector<int64_t> sn_lptr;     // [nsuper+1] into the panel storage (column-major, ld = sn_nrow)
+  std::vector<int64_t> sn_lptr;     // [nsuper+1] into the panel storage (column-major, ld = panel_ld(sn_nrow))
   std::vector<int32_t> rows;        // concatenated sorted row lists
   std::vector<int32_t> rel;         // aligned with rows[]: position of a below-row inside the parent's row list
   std::vector<int32_t> col2sn;      // [n]

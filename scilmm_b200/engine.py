@@ -98,6 +98,8 @@ class SymbolicView(object):
         order = ["perm", "parent", "colcount", "sn_first", "sn_nrow", "sn_parent", "sn_rowptr", "sn_lptr", "rows",
                  "rel", "level_ptr", "level_sn"]
         check(lib().slmm_symbolic_arrays(self._h, *[np_ptr(out[k]) for k in order]))
+        # leading dimension of every panel: rows rounded up to even (csrc/symbolic.h panel_ld: 16-byte aligned columns)
+        out["sn_ld"] = ((out["sn_nrow"].astype(np.int64) + 1) & ~np.int64(1)).astype(np.int64)
         return out
 
     def entry_map(self, pattern):
@@ -523,7 +525,7 @@ class CholEngine(object):
         check(lib().slmm_chol_aux_join(self._h))
 
     def panels(self):
-        """Raw supernodal panels as one host array (layout: SymbolicView.arrays() sn_lptr / sn_nrow)."""
+        """Raw supernodal panels as one host array (layout: SymbolicView.arrays() sn_lptr / sn_ld / sn_nrow)."""
         out = np.zeros(self.stats()["lsize"], dtype=np.float64)
         check(lib().slmm_chol_copy_panels(self._h, np_ptr(out)))
         return out
@@ -556,11 +558,11 @@ class CholEngine(object):
 
     def profile(self):
         """Per-kernel-kind device time (ms), issued flops and launch counts since set_profiling(True)."""
-        ms, fl, n = np.zeros(12), np.zeros(12), np.zeros(12, dtype=np.int64)
-        check(lib().slmm_chol_get_profile_ex(self._h, 12, np_ptr(ms), np_ptr(fl), np_ptr(n)))
+        ms, fl, n = np.zeros(13), np.zeros(13), np.zeros(13, dtype=np.int64)
+        check(lib().slmm_chol_get_profile_ex(self._h, 13, np_ptr(ms), np_ptr(fl), np_ptr(n)))
         names = ["potrf_inv", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big", "init_w",
-                 "splitk_reduce", "_ev_record", "_ev_wait", "skinny_f1", "skinny_f2"]
-        return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(12)
+                 "splitk_reduce", "_ev_record", "_ev_wait", "skinny_f1", "skinny_f2", "gemm_tma"]
+        return {names[k]: dict(ms=float(ms[k]), flops=float(fl[k]), launches=int(n[k])) for k in range(13)
                 if not names[k].startswith("_")}
 
     def launch_profile(self):

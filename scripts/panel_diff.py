@@ -30,8 +30,9 @@ for rep in range(2):
     bad = []
     for s in range(nsuper):
         ns, ms = first[s + 1] - first[s], nrow[s]
-        g = Lx[lptr[s]:lptr[s] + ms * ns].reshape((ms, ns), order='F')
-        r = ref.Lx[lptr[s]:lptr[s] + ms * ns].reshape((ms, ns), order='F')
+        ld = int(a['sn_ld'][s])
+        g = Lx[lptr[s]:lptr[s] + ld * ns].reshape((ld, ns), order='F')[:ms]
+        r = ref.Lx[lptr[s]:lptr[s] + ld * ns].reshape((ld, ns), order='F')[:ms]
         m = np.tril(np.ones((min(ms, ns), ns), bool))
         diff = np.abs(g - r)
         diff[:ns][~m[:ns]] = 0

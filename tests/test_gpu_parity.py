@@ -35,7 +35,8 @@ def eng():
 @pytest.mark.parametrize("M,N,K,lower", [(64, 64, 64, False), (128, 128, 16, False), (200, 150, 37, False),
                                          (513, 257, 130, False), (300, 300, 64, True), (1000, 40, 64, False),
                                          (7, 5, 3, False), (140, 777, 64, False), (128, 200, 5000, False),
-                                         (140, 60, 20011, False)])
+                                         (140, 60, 20011, False), (1024, 1024, 1024, False), (2000, 1500, 300, True),
+                                         (640, 384, 96, False), (258, 130, 64, False)])
 def test_dmma_gemm_tiles(eng, M, N, K, lower):
     err, ms, tf = eng.gemm_selftest(M, N, K, lower=lower, reps=1)
     assert err < 1e-11 * max(K, 1), (err, M, N, K)
@@ -482,8 +483,9 @@ def test_pedigree_scale_factor_vs_oracle_panels(slmm, eng):
     worst = 0.0
     for s_ in range(len(nrow)):
         ns, ms = first[s_ + 1] - first[s_], nrow[s_]
-        g = L2[lptr[s_]:lptr[s_] + ms * ns].reshape((ms, ns), order='F')
-        r = ref.Lx[lptr[s_]:lptr[s_] + ms * ns].reshape((ms, ns), order='F')
+        ld = int(a['sn_ld'][s_])
+        g = L2[lptr[s_]:lptr[s_] + ld * ns].reshape((ld, ns), order='F')[:ms]
+        r = ref.Lx[lptr[s_]:lptr[s_] + ld * ns].reshape((ld, ns), order='F')[:ms]
         d = np.abs(g - r)
         d[:ns][np.triu(np.ones((ns, ns), bool), 1)] = 0.0          # strict upper part of the diagonal block is unused
         worst = max(worst, float(d.max()))

@@ -42,7 +42,8 @@ def emulate_plan(V, sym):
             rs = ms - ns
             rows = a['rows'][a['sn_rowptr'][s]:a['sn_rowptr'][s + 1]]
             assert np.array_equal(rows[:ns], np.arange(f, f + ns)) and np.all(np.diff(rows) > 0)
-            P = Lx[a['sn_lptr'][s]:a['sn_lptr'][s + 1]].reshape(ns, ms).T.copy()
+            ld = int(a['sn_ld'][s])          # panels are padded to an even number of rows
+            P = Lx[a['sn_lptr'][s]:a['sn_lptr'][s + 1]].reshape(ns, ld).T[:ms].copy()
             F22 = np.zeros((rs, rs))
             for c in children[s]:
                 nsc = a['sn_first'][c + 1] - a['sn_first'][c]
