@@ -617,13 +617,17 @@ def bench_he(args, E, P, S, torch, hbm, barrier, max_over_ranks):
     e2e_s = 1e30
     for _ in range(2):          # best of two public calls (host page-locking / allocator noise on a shared box)
         barrier()
+        S.HE_TIMINGS = {}
         t0 = time.perf_counter()
         est = S.HE(list(mats), cov, y.copy())
         torch.cuda.synchronize()
-        e2e_s = min(e2e_s, max_over_ranks(time.perf_counter() - t0))
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if dt < e2e_s:
+            e2e_s, e2e_parts = dt, {k: round(v, 4) for k, v in S.HE_TIMINGS.items()}
+        S.HE_TIMINGS = None
     out = {"workload": "HE fit, simulated pedigree %d (sf=%g), K=3 (IBD, AoA, household)" % (args.he_n, args.he_sf),
            **info, "nnz_household": int(H.nnz), "n_gpus": world, "device_ms": round(dev_ms, 4),
-           "e2e_s": round(e2e_s, 3), "h2d_bytes_per_rank": h2d_local, "rows_this_rank": [lo, hi],
+           "e2e_s": round(e2e_s, 3), "e2e_parts_s": e2e_parts, "h2d_bytes_per_rank": h2d_local, "rows_this_rank": [lo, hi],
            "estimates": [float(v) for v in est],
            "roofline": {"bound": "hbm", "kernel": "he_group_kernel<2> (IBD + AoA, lower triangle) + he_short_kernel (household) + "
                                   "he_cross_mapped_kernel<1,2> + reduce_all_kernel",

@@ -267,6 +267,12 @@ int slmm_ibd_destroy(slmm_ibd_t* h);
 int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,
                        int32_t lower, int32_t reps, float* ms_out);
 
+/* `copies` identical operations C_c (+/-)= A B^T in one launch, column-major operands with explicit leading
+ * dimensions (C_c = d_C + c*ldc*N); flags: 1 lower-masked, 2 accumulate, 4 negate.  Test hook for the tile kernels
+ * (several ops per launch, panel-like strides, operands that start on an odd element). */
+int slmm_gemm_selftest_ex(int32_t M, int32_t N, int32_t K, const double* d_A, int64_t lda, const double* d_B, int64_t ldb,
+                          double* d_C, int64_t ldc, int32_t flags, int32_t copies);
+
 #ifdef __cplusplus
 }
 #endif

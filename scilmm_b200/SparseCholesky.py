@@ -582,6 +582,9 @@ def REML(cholesky_func, mats, covariates, y, reml=True, sim_num=100, verbose=Fal
 
 
 # ------------------------------------------------------------------------------------------- Haseman-Elston
+HE_TIMINGS = None      # set to a dict to collect the phases of the next he_moments call (upload / kernels)
+
+
 def he_moments(mat_list, y, MQS=False, matset=None):
     """q and S of the HE normal equations on the GPU (reference :213-243).
 
@@ -590,6 +593,7 @@ def he_moments(mat_list, y, MQS=False, matset=None):
     computes its partial moments, and one all-reduce of 2K + 2K^2 doubles combines them."""
     torch = _eng.require_cuda()
     rank, world = _shard.rank_world()
+    t0 = time.time()
     if matset is not None:
         ms = matset
     elif world == 1:
@@ -600,6 +604,10 @@ def he_moments(mat_list, y, MQS=False, matset=None):
         ms = _eng.MatSet(mat_list, row_range=(int(bounds[rank]), int(bounds[rank + 1])))
     K, n = ms.K, ms.n
     y_dev = _eng.to_device(np.asarray(y, dtype=np.float64), torch)
+    if HE_TIMINGS is not None:
+        torch.cuda.synchronize()
+        HE_TIMINGS["upload_s"] = time.time() - t0
+        t0 = time.time()
     if ms.row_range == (0, n) and world == 1:
         out = ms.he_moments_device(y_dev).cpu().numpy()
     elif ms.row_range == (0, n):      # whole matrices on every rank (caller-supplied set): shard the rows only
@@ -611,6 +619,8 @@ def he_moments(mat_list, y, MQS=False, matset=None):
         ms.resolve_symmetry_sharded(_shard.allreduce_sum_)
         part = ms.he_moments_device(y_dev).clone()
         out = _shard.allreduce_sum_(part).cpu().numpy()
+    if HE_TIMINGS is not None:
+        HE_TIMINGS["moments_s"] = time.time() - t0
     q_off, q_diag, S_off, S_diag = _eng.MatSet.split_moments(out, K)
     if MQS:
         yy = float(np.dot(y, y))

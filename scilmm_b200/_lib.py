@@ -98,6 +98,7 @@ SIGNATURES = {
     "slmm_ibd_copy_DF": (C.c_int, [vp, vp, vp]),
     "slmm_ibd_copy_A": (C.c_int, [vp, vp, vp, vp]),
     "slmm_ibd_destroy": (C.c_int, [vp]),
+    "slmm_gemm_selftest_ex": (C.c_int, [i32, i32, i32, vp, i64, vp, i64, vp, i64, i32, i32]),
     "slmm_gemm_selftest": (C.c_int, [i32, i32, i32, vp, vp, vp, i32, i32, C.POINTER(C.c_float)]),
 }
 

@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
     objs = []
     for src in SOURCES_CPP:
         obj = os.path.join(HERE, src.replace(".cpp", ".o"))
-        cmd = ["g++", "-O2", "-fPIC", "-pthread", "-std=c++17", "-c", os.path.join(HERE, src), "-o", obj]
+        cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-c", os.path.join(HERE, src), "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

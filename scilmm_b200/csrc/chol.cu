@@ -1875,6 +1875,27 @@ int slmm_symbolic_entry_map(const slmm_symbolic_t* h, const int32_t* indptr, con
   SLMM_CATCH
 }
 
+int slmm_gemm_selftest_ex(int32_t M, int32_t N, int32_t K, const double* d_A, int64_t lda, const double* d_B, int64_t ldb,
+                          double* d_C, int64_t ldc, int32_t flags, int32_t copies) {
+  SLMM_TRY
+  // `copies` identical ops C (+/-)= A B' in ONE launch (several ops per launch, as in the factorization); column-major
+  // operands with explicit leading dimensions, so that panel-like strides and odd base offsets can be exercised
+  init_kernel_attributes();
+  Schedule sch;
+  PhaseBuilder pb;
+  pb.allow_split = false;
+  for (int c = 0; c < copies; c++)
+    pb.add(make_op(d_C + (int64_t)c * ldc * N, 1, ldc, d_A, 1, lda, d_B, 1, ldb, M, N, K, flags & (GF_LOWER | GF_ACCUM | GF_NEG)));
+  pb.flush(sch);
+  sch.upload();
+  slmm_chol dummy;
+  run_schedule(&dummy, sch, nullptr, nullptr, nullptr, 0);
+  CUDA_OK(cudaDeviceSynchronize());
+  sch.release();
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
 int slmm_gemm_selftest(int32_t M, int32_t N, int32_t K, const double* d_A, const double* d_B, double* d_C,
                        int32_t lower, int32_t reps, float* ms_out) {
   SLMM_TRY

@@ -13,6 +13,7 @@
 // Everything is accumulated in a fixed order (tiles are assigned to CTAs by a static partition, rows to warps by
 // index): results are bit-reproducible.  The tiling is built once per session on the device (two radix sorts).
 #include <algorithm>
+#include <cassert>
 #include <cstring>
 #include <vector>
 
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) qt_keys2_kernel(const uint64_t* __restric
     const int rb = (int)(key >> 34), pj = (int)((key >> 6) & 0xfffffffull), lrow = (int)(key & 63);
     const int g = gidx[e] - 1;                       // global index of the (row block, column) pair
     const int dcol = g - dcol_base[rb];
+    assert(dcol >= 0);
     const int tile = tile_base[rb] + dcol / QT_CH, lcol = dcol % QT_CH;
     const int diag = (rb * QT_RB + lrow) == pj ? 1 : 0;
     keys2[e] = ((uint64_t)tile << 13) | ((uint64_t)lrow << 7) | ((uint64_t)lcol << 1) | (uint64_t)diag;
@@ -120,13 +122,18 @@ __global__ void __launch_bounds__(256) qt_pack_kernel(const uint64_t* __restrict
 }
 
 __global__ void __launch_bounds__(256) qt_values_kernel(const uint16_t* __restrict__ rc, const uint32_t* __restrict__ pos,
-                                                        const double* __restrict__ data, int64_t m, double* __restrict__ out) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x)
+                                                        const double* __restrict__ data, int64_t m, int64_t nnz,
+                                                        double* __restrict__ out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x) {
+    assert((int64_t)pos[e] < nnz);
     out[e] = ((rc[e] & 1) ? 1.0 : 2.0) * data[pos[e]];          // off-diagonal entries stand for both triangles
+  }
 }
 
 // ---- the pass ---------------------------------------------------------------------------------------------------
 struct QtArgs {
+  int64_t nentries, ndistinct;
+  int32_t ntiles, nrb, n, pad;
   const int64_t* tile_ptr;
   const int32_t *tile_rb, *tile_dc0, *tile_nc, *dcols, *rowid, *cta_begin;
   const uint16_t *rowptr, *rc;
@@ -156,12 +163,16 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     for (int c = 0; c < CPL; c++) dot[g][c] = 0.0;
   for (int q = tid; q < QT_CH * LDX + QT_RB * G * QT_NB + G * QT_NB * QT_NB; q += 256) qsm[q] = 0.0;   // incl. the padding columns of Xs
   __syncthreads();
+  assert(t_begin >= 0 && t_begin <= t_end && t_end <= a.ntiles);
   for (int t = t_begin; t < t_end; t++) {
     const int rb = a.tile_rb[t], nc = a.tile_nc[t], dc0 = a.tile_dc0[t];
     const int64_t tb = a.tile_ptr[t];
+    assert(rb >= 0 && rb < a.nrb && nc > 0 && nc <= QT_CH && dc0 >= 0 && (int64_t)dc0 + nc <= a.ndistinct);
+    assert(tb >= 0 && a.tile_ptr[t + 1] >= tb && a.tile_ptr[t + 1] <= a.nentries);
     // stage the tile: row starts + the nc gathered rows of X
     if (tid <= QT_RB) rp_s[tid] = a.rowptr[(int64_t)t * (QT_RB + 1) + tid];
     for (int c = warp; c < nc; c += 8) {
+      assert(a.dcols[dc0 + c] >= 0 && a.dcols[dc0 + c] < a.n);
       const double* src = X + (int64_t)a.dcols[dc0 + c] * ncx;
       double* dst = Xs + c * LDX;
       for (int j = lane; j < ncx; j += 32) qt_cp_async8(dst + j, src + j);
@@ -170,6 +181,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     __syncthreads();
     for (int lr = warp; lr < QT_RB; lr += 8) {
       const int e0 = rp_s[lr], e1 = rp_s[lr + 1];
+      assert(e0 <= e1 && tb + e1 <= a.tile_ptr[t + 1]);
       if (e0 == e1) continue;
       double acc[G][CPL];
 #pragma unroll
@@ -185,6 +197,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
         const int cnt = min(32, e1 - p0);
         for (int k = 0; k < cnt; k++) {
           const int lcol = __shfl_sync(0xffffffffu, myrc, k) >> 1;
+          assert(lcol >= 0 && lcol < nc);
           double v[G];
 #pragma unroll
           for (int g = 0; g < G; g++) v[g] = __shfl_sync(0xffffffffu, myv[g], k);
@@ -198,6 +211,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
         }
       }
       const int row = a.rowid[rb * QT_RB + lr];
+      assert(row >= 0 && row < a.n);
       const double* xi = X + (int64_t)row * ncx + lane;
 #pragma unroll
       for (int c = 0; c < CPL; c++) {
@@ -420,7 +434,8 @@ int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm,
   for (int q : T.vals_of) have = have || q == k;
   if (!have) {
     double* v = dev_alloc<double>((size_t)T.nentries);
-    qt_values_kernel<<<(int)std::min<int64_t>((T.nentries + 255) / 256, 148 * 16), 256>>>(T.rc, T.pos, ms->m[k].data, T.nentries, v);
+    qt_values_kernel<<<(int)std::min<int64_t>((T.nentries + 255) / 256, 148 * 16), 256>>>(T.rc, T.pos, ms->m[k].data, T.nentries, ms->m[k].nnz, v);
+    CUDA_OK(cudaDeviceSynchronize());
     g_launch_count++;
     T.vals.push_back(v);
     T.vals_of.push_back(k);
@@ -448,6 +463,7 @@ int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
   if (it == ms->tiles.end() || it->second.ntiles == 0) throw std::invalid_argument("build the tiles first (slmm_matset_build_tiles)");
   QuadTiles& T = it->second;
   QtArgs a;
+  a.nentries = T.nentries; a.ndistinct = T.ndistinct; a.ntiles = T.ntiles; a.nrb = T.nrb; a.n = ms->n; a.pad = 0;
   a.tile_ptr = T.tile_ptr; a.tile_rb = T.tile_rb; a.tile_dc0 = T.tile_dc0; a.tile_nc = T.tile_nc; a.dcols = T.dcols;
   a.rowid = T.rowid; a.cta_begin = T.cta_begin; a.rowptr = T.rowptr; a.rc = T.rc;
   for (int g = 0; g < nk; g++) {

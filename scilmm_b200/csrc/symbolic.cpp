@@ -8,12 +8,9 @@
 #include <chrono>
 #include <cstring>
 #include <numeric>
+#include <cstdio>
 #include <stdexcept>
-#include <thread>
-#include <unordered_map>
 
-extern "C" int METIS_ComputeVertexSeparator(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
-                                            int64_t* sepsize, int64_t* part);
 extern "C" int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
                             int64_t* perm, int64_t* iperm);
 extern "C" int METIS_SetDefaultOptions(int64_t* options);
@@ -60,143 +57,6 @@ void small_mindeg(int m, const std::vector<std::vector<int>>& adj, std::vector<i
     }
     std::fill(row(best), row(best) + W, 0ull);
   }
-}
-
-// ---- nested dissection of one large component on several host threads -------------------------------------
-// METIS_NodeND is serial (8 s of a 9 s session set-up at the 250K config).  Its recursion is restated one level up:
-// indistinguishable vertices (identical closed neighbourhoods: full siblings without descendants in a pedigree) are
-// merged into weighted vertices first (what METIS' own COMPRESS option does inside NodeND), the top `depth` levels
-// of separators come from METIS_ComputeVertexSeparator (same multilevel bisection, same UFACTOR / NSEPS options), and
-// the 2^depth subgraphs are then ordered by METIS_NodeND concurrently.  Elimination order: left, right, separator.
-struct NdGraph {
-  int64_t n = 0;
-  std::vector<int64_t> xadj, adjncy, vwgt;
-};
-
-void nd_recursive(NdGraph& G, int depth, int maxdepth, int64_t* options, std::vector<int64_t>& order) {
-  order.resize(G.n);
-  if (G.n == 0) return;
-  if (depth >= maxdepth || G.n < 4000) {
-    std::vector<int64_t> perm(G.n), iperm(G.n);
-    int64_t nv = G.n;
-    const int rc = METIS_NodeND(&nv, G.xadj.data(), G.adjncy.data(), G.vwgt.data(), options, perm.data(), iperm.data());
-    if (rc != 1) throw std::runtime_error("METIS_NodeND failed");
-    for (int64_t k = 0; k < G.n; k++) order[k] = perm[k];          // perm[new] = old
-    return;
-  }
-  std::vector<int64_t> part(G.n);
-  int64_t nv = G.n, sepsize = 0;
-  const int rc = METIS_ComputeVertexSeparator(&nv, G.xadj.data(), G.adjncy.data(), G.vwgt.data(), options, &sepsize, part.data());
-  if (rc != 1) throw std::runtime_error("METIS_ComputeVertexSeparator failed");
-  NdGraph sub[2];
-  std::vector<int64_t> local(G.n, -1), members[3];
-  for (int64_t v = 0; v < G.n; v++) {
-    const int p = (int)part[v];
-    if (p < 2) local[v] = (int64_t)members[p].size();
-    members[p < 0 || p > 2 ? 2 : p].push_back(v);
-  }
-  for (int p = 0; p < 2; p++) {
-    NdGraph& H = sub[p];
-    H.n = (int64_t)members[p].size();
-    H.xadj.assign(H.n + 1, 0);
-    H.vwgt.resize(H.n);
-    int64_t cnt = 0;
-    for (int64_t k = 0; k < H.n; k++) {
-      const int64_t v = members[p][k];
-      H.vwgt[k] = G.vwgt[v];
-      for (int64_t q = G.xadj[v]; q < G.xadj[v + 1]; q++) cnt += part[G.adjncy[q]] == p;
-      H.xadj[k + 1] = cnt;
-    }
-    H.adjncy.resize(cnt);
-    cnt = 0;
-    for (int64_t k = 0; k < H.n; k++) {
-      const int64_t v = members[p][k];
-      for (int64_t q = G.xadj[v]; q < G.xadj[v + 1]; q++)
-        if (part[G.adjncy[q]] == p) H.adjncy[cnt++] = local[G.adjncy[q]];
-    }
-  }
-  { NdGraph empty; std::swap(G.adjncy, empty.adjncy); }             // the parent's edges are no longer needed
-  std::vector<int64_t> o[2];
-  std::exception_ptr err;
-  std::thread t([&] {
-    try { nd_recursive(sub[0], depth + 1, maxdepth, options, o[0]); } catch (...) { err = std::current_exception(); }
-  });
-  nd_recursive(sub[1], depth + 1, maxdepth, options, o[1]);
-  t.join();
-  if (err) std::rethrow_exception(err);
-  int64_t out = 0;
-  for (int p = 0; p < 2; p++)
-    for (int64_t k = 0; k < sub[p].n; k++) order[out++] = members[p][o[p][k]];
-  for (int64_t v : members[2]) order[out++] = v;
-}
-
-// order[k] = local vertex eliminated k-th.  xadj/adjncy: the component's graph without self loops (local ids).
-void parallel_nd(int m, const std::vector<int64_t>& xadj, const std::vector<int64_t>& adjncy, int64_t* options, int maxdepth,
-                 std::vector<int64_t>& order) {
-  // compress indistinguishable vertices: equal hash of the sorted closed neighbourhood, then exact comparison
-  std::vector<uint64_t> hsh(m);
-  std::vector<int64_t> nb;
-  auto closed = [&](int v, std::vector<int64_t>& out) {
-    out.assign(adjncy.begin() + xadj[v], adjncy.begin() + xadj[v + 1]);
-    out.push_back(v);
-    std::sort(out.begin(), out.end());
-  };
-  for (int v = 0; v < m; v++) {
-    uint64_t h = 1469598103934665603ull, sum = (uint64_t)v * 0x9E3779B97F4A7C15ull;
-    for (int64_t q = xadj[v]; q < xadj[v + 1]; q++) sum += (uint64_t)adjncy[q] * 0x9E3779B97F4A7C15ull;   // order independent
-    h ^= sum; h *= 1099511628211ull; h ^= (uint64_t)(xadj[v + 1] - xadj[v]);
-    hsh[v] = h;
-  }
-  std::unordered_map<uint64_t, std::vector<int>> buckets;
-  buckets.reserve(m);
-  for (int v = 0; v < m; v++) buckets[hsh[v]].push_back(v);
-  std::vector<int64_t> rep(m, -1);
-  std::vector<int64_t> a, b;
-  for (int v = 0; v < m; v++) {
-    if (rep[v] >= 0) continue;
-    rep[v] = v;
-    std::vector<int>& cand = buckets[hsh[v]];
-    if (cand.size() < 2) continue;
-    closed(v, a);
-    for (int u : cand) {
-      if (u <= v || rep[u] >= 0 || xadj[u + 1] - xadj[u] != xadj[v + 1] - xadj[v]) continue;
-      closed(u, b);
-      if (a == b) rep[u] = v;
-    }
-  }
-  std::vector<int64_t> cid(m, -1);
-  NdGraph G;
-  std::vector<std::vector<int>> groups;
-  for (int v = 0; v < m; v++)
-    if (rep[v] == v) { cid[v] = G.n++; groups.emplace_back(); }
-  for (int v = 0; v < m; v++) { cid[v] = cid[rep[v]]; groups[cid[v]].push_back(v); }
-  G.vwgt.resize(G.n);
-  G.xadj.assign(G.n + 1, 0);
-  std::vector<int64_t> mark(G.n, -1);
-  for (int pass = 0; pass < 2; pass++) {
-    int64_t cnt = 0;
-    std::fill(mark.begin(), mark.end(), -1);
-    for (int64_t c = 0; c < G.n; c++) {
-      const int v = groups[c][0];
-      G.vwgt[c] = (int64_t)groups[c].size();
-      mark[c] = c;
-      for (int64_t q = xadj[v]; q < xadj[v + 1]; q++) {
-        const int64_t d = cid[adjncy[q]];
-        if (mark[d] == c) continue;
-        mark[d] = c;
-        if (pass) G.adjncy[cnt] = d;
-        cnt++;
-      }
-      if (!pass) G.xadj[c + 1] = cnt;
-    }
-    if (!pass) G.adjncy.resize(cnt);
-  }
-  std::vector<int64_t> corder;
-  nd_recursive(G, 0, maxdepth, options, corder);
-  order.clear();
-  order.reserve(m);
-  for (int64_t c : corder)
-    for (int v : groups[c]) order.push_back(v);
 }
 
 // ---- ordering -----------------------------------------------------------------------------------------
@@ -304,18 +164,6 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
     options[16] = 10;   // METIS_OPTION_UFACTOR
     options[15] = 3;    // METIS_OPTION_NSEPS
     for (const auto& kv : opt_metis) options[kv.first] = kv.second;
-    // large components: top separator levels by hand, subgraphs ordered concurrently (SLMM_ND_DEPTH levels, default
-    // 3 -> 8 threads; 0 = plain serial METIS_NodeND)
-    int nd_depth = 3;
-    if (const char* env = getenv("SLMM_ND_DEPTH")) nd_depth = atoi(env);
-    if (std::thread::hardware_concurrency() < 2) nd_depth = 0;
-    if (m >= 20000 && nd_depth > 0) {
-      std::vector<int64_t> order;
-      parallel_nd(m, xadj, adjncy, options, nd_depth, order);
-      if ((int)order.size() != m) throw std::runtime_error("parallel nested dissection lost vertices");
-      for (int k = 0; k < m; k++) perm[out++] = queue[b + order[k]];
-      continue;
-    }
     int rc = METIS_NodeND(&nv, xadj.data(), adjncy.data(), nullptr, options, mperm.data(), miperm.data());
     if (rc != 1) throw std::runtime_error("METIS_NodeND failed");
     // METIS: A' = A(perm, perm); perm[new] = old
@@ -324,11 +172,14 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
   if (out != n) throw std::runtime_error("ordering lost vertices");
 }
 
-// permuted full symmetric pattern, sorted rows, without the diagonal
+// permuted full symmetric pattern, sorted rows, without the diagonal.
+// No sorting: the pattern is symmetric, so the permuted matrix equals its transpose, and a transpose built by walking
+// the new rows i = 0..n-1 in order and appending i to the list of every new column j it touches comes out with
+// sorted lists (one counting pass + one scatter pass over the entries instead of 6e7 entries of std::sort).
 void permute_pattern(int n, const int32_t* ap, const int32_t* ai, const std::vector<int32_t>& perm,
                      const std::vector<int32_t>& iperm, std::vector<int64_t>& bp, std::vector<int32_t>& bi) {
   bp.assign(n + 1, 0);
-  for (int i = 0; i < n; i++) {
+  for (int i = 0; i < n; i++) {            // by symmetry the list of new column i is as long as new row i
     int o = perm[i];
     int64_t c = 0;
     for (int p = ap[o]; p < ap[o + 1]; p++)
@@ -336,12 +187,37 @@ void permute_pattern(int n, const int32_t* ap, const int32_t* ai, const std::vec
     bp[i + 1] = bp[i] + c;
   }
   bi.resize(bp[n]);
+  std::vector<int64_t> fill(bp.begin(), bp.end() - 1);
   for (int i = 0; i < n; i++) {
     int o = perm[i];
-    int64_t q = bp[i];
-    for (int p = ap[o]; p < ap[o + 1]; p++)
-      if (ai[p] != o) bi[q++] = iperm[ai[p]];
-    std::sort(bi.begin() + bp[i], bi.begin() + bp[i + 1]);
+    for (int p = ap[o]; p < ap[o + 1]; p++) {
+      if (ai[p] == o) continue;
+      const int j = iperm[ai[p]];
+      if (fill[j] >= bp[j + 1]) throw std::runtime_error("the pattern is not structurally symmetric");
+      bi[fill[j]++] = i;
+    }
+  }
+  for (int j = 0; j < n; j++)
+    if (fill[j] != bp[j + 1]) throw std::runtime_error("the pattern is not structurally symmetric");
+}
+
+// elimination tree of the permuted matrix straight from the original pattern (Liu's algorithm needs the entries of a
+// column in no particular order, so nothing has to be permuted or sorted for it)
+void etree_permuted(int n, const int32_t* ap, const int32_t* ai, const std::vector<int32_t>& perm,
+                    const std::vector<int32_t>& iperm, std::vector<int32_t>& parent) {
+  parent.assign(n, -1);
+  std::vector<int32_t> anc(n, -1);
+  for (int j = 0; j < n; j++) {
+    const int o = perm[j];
+    for (int p = ap[o]; p < ap[o + 1]; p++) {
+      int i = iperm[ai[p]];
+      while (i != -1 && i < j) {
+        int nx = anc[i];
+        anc[i] = j;
+        if (nx == -1) parent[i] = j;
+        i = nx;
+      }
+    }
   }
 }
 
@@ -446,18 +322,23 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
   }
   S.t_order = now_s() - t0;
   t0 = now_s();
+  const bool timing = getenv("SLMM_SYM_TIMING") != nullptr;
+  double tp = now_s();
+  auto lap = [&](const char* what) { if (timing) { fprintf(stderr, "[symbolic] %-28s %.3f s\n", what, now_s() - tp); tp = now_s(); } };
 
   std::vector<int32_t> iperm0(n);
   for (int i = 0; i < n; i++) iperm0[perm0[i]] = i;
   std::vector<int64_t> bp;
   std::vector<int32_t> bi, par0, post;
   const bool keep_order = (opt.ordering == ORD_GIVEN || opt.ordering == ORD_NATURAL);
-  permute_pattern(n, ap, ai, perm0, iperm0, bp, bi);
-  etree(n, bp, bi, par0);
+  etree_permuted(n, ap, ai, perm0, iperm0, par0);
   postorder(n, par0, post);
+  lap("etree + postorder");
   bool is_post = true;
   for (int k = 0; k < n; k++) if (post[k] != k) { is_post = false; break; }
   if (is_post || keep_order) {
+    permute_pattern(n, ap, ai, perm0, iperm0, bp, bi);
+    lap("permute_pattern");
     // A user-supplied / natural order is kept verbatim (parity mode: L is unique given P).  It is only
     // usable directly when it is already a postorder of its own etree; otherwise supernodes degrade to
     // those contiguous column runs that are chains, which is still correct.
@@ -470,8 +351,10 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
     S.iperm.resize(n);
     for (int i = 0; i < n; i++) S.iperm[S.perm[i]] = i;
     permute_pattern(n, ap, ai, S.perm, S.iperm, bp, bi);
+    lap("permute_pattern #2");
     etree(n, bp, bi, S.parent);
     is_post = true;
+    lap("etree #2");
   }
   if (is_post) {
     column_counts(n, bp, bi, S.parent, S.colcount);
@@ -490,6 +373,7 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
     S.colcount.resize(n);
     for (int j = 0; j < n; j++) S.colcount[j] = pcc[ipost[j]];
   }
+  lap("column counts");
   const std::vector<int32_t>& parent = S.parent;
   const std::vector<int32_t>& cc = S.colcount;
   S.nnzL = 0;
@@ -576,6 +460,7 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
     std::vector<int32_t> fill(S.child_ptr.begin(), S.child_ptr.end() - 1);
     for (int s = 0; s < S.nsuper; s++) if (S.sn_parent[s] >= 0) S.child_idx[fill[S.sn_parent[s]]++] = s;
   }
+  lap("supernodes + amalgamation");
   // ---- supernodal row structures (children before parents: supernode ids ascend with columns)
   S.sn_rowptr.assign(S.nsuper + 1, 0);
   S.sn_nrow.assign(S.nsuper, 0);
@@ -612,6 +497,7 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
     S.max_super_cols = std::max(S.max_super_cols, ns);
   }
   S.lsize = S.sn_lptr[S.nsuper];
+  lap("row structures");
   // relative indices into the parent's row list (merge of two sorted lists)
   for (int s = 0; s < S.nsuper; s++) {
     int p = S.sn_parent[s];
@@ -625,6 +511,7 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
       S.rel[a] = (int32_t)(b - S.sn_rowptr[p]);
     }
   }
+  lap("relative indices");
   // ---- depth levels
   S.sn_depth.assign(S.nsuper, 0);
   int maxd = 0;

@@ -494,3 +494,42 @@ def test_pedigree_scale_factor_vs_oracle_panels(slmm, eng):
     B = np.random.default_rng(3).standard_normal((n, 70))
     X = ses.eng.solve_(eng.to_device(B)).cpu().numpy()
     assert np.abs(V.dot(X) - B).max() < 1e-10 * np.abs(B).max()
+
+
+@pytest.mark.parametrize("M,N,K,lda,ldb,offa,offb,flags,copies", [
+    (512, 384, 256, 512, 384, 0, 0, 0, 1),          # plain
+    (512, 384, 256, 800, 800, 0, 0, 0, 1),          # panel-like leading dimensions
+    (512, 384, 256, 800, 800, 0, 0, 0, 3),          # several ops in one launch
+    (512, 384, 256, 800, 800, 1, 1, 0, 1),          # operands starting on an odd element (tensor-map base rounded down)
+    (513, 259, 96, 802, 802, 1, 0, 0, 2),
+    (736, 236, 64, 800, 800, 64, 64, 1 | 2 | 4, 1),  # lower-masked accumulate-negate: the in-block update of a narrow front
+    (700, 700, 300, 1000, 1000, 301, 301, 1 | 4, 1),  # Schur complement of a front with an odd number of columns
+])
+def test_dmma_gemm_tiles_strided_multi_op(eng, M, N, K, lda, ldb, offa, offb, flags, copies):
+    """The tile GEMMs (TMA-staged and cp.async-staged) on panel-shaped operands: explicit leading dimensions, odd base
+    offsets, several operations per launch, lower / accumulate / negate."""
+    import ctypes as C
+    import torch
+    from scilmm_b200._lib import check, lib
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Abuf = torch.randn(K * lda + offa + 8, generator=g, dtype=torch.float64, device="cuda")
+    Bbuf = torch.randn(K * ldb + offb + 8, generator=g, dtype=torch.float64, device="cuda")
+    ldc = M + 2
+    C0 = torch.randn(copies, N, ldc, generator=g, dtype=torch.float64, device="cuda")
+    Cd = C0.clone()
+    check(lib().slmm_gemm_selftest_ex(M, N, K, Abuf.data_ptr() + 8 * offa, lda, Bbuf.data_ptr() + 8 * offb, ldb,
+                                      Cd.data_ptr(), ldc, flags, copies))
+    A = Abuf[offa:offa + K * lda].view(K, lda)[:, :M]           # A[k, i] = A(i, k)
+    B = Bbuf[offb:offb + K * ldb].view(K, ldb)[:, :N]
+    P = (A.t() @ B).t()                                         # [N, M]: P[j, i] = sum_k A(i,k) B(j,k)
+    if flags & 4:
+        P = -P
+    want = C0.clone()
+    upd = (want[:, :, :M] + P) if (flags & 2) else P.expand(copies, N, M)
+    if flags & 1:
+        mask = (torch.arange(M, device="cuda")[None, :] >= torch.arange(N, device="cuda")[:, None])
+        upd = torch.where(mask, upd, want[:, :, :M])
+    want[:, :, :M] = upd
+    assert torch.equal(Cd[:, :, M:], C0[:, :, M:])              # nothing written outside the M rows
+    err = (Cd - want).abs().max().item()
+    assert err < 1e-11 * K, err
