@@ -520,8 +520,9 @@ def _hess_device(ses, factor_eng, pre=None):
     Py = project_solved(Viy.unsqueeze(1))
     AjPy = torch.cat([ses.matset.spmm(j, Py) for j in range(K)], dim=1)       # n x K
     PAjPy = project(AjPy)
-    pairs = [(i, j) for j in range(K) for i in range(j + 1)]
-    cols = torch.cat([ses.matset.spmm(i, PAjPy[:, j:j + 1].contiguous()) for (i, j) in pairs], dim=1)
+    pairs = [(i, j) for i in range(K) for j in range(i, K)]
+    # A_i (P A_j P y) for all j >= i in ONE pass over A_i (a block of K - i columns)
+    cols = torch.cat([ses.matset.spmm(i, PAjPy[:, i:].contiguous()) for i in range(K)], dim=1)
     vals = (-0.5 * (y @ project(cols))).cpu().numpy()
     hess = np.empty((K, K))
     for q, (i, j) in enumerate(pairs):

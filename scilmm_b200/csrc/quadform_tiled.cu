@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) qt_tileptr_kernel(const uint64_t* __restr
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t tile = q / (QT_RB + 1);
     const int lr = (int)(q % (QT_RB + 1));
-    const uint64_t want = ((uint64_t)tile << 13) | ((uint64_t)lr << 7);
+    const uint64_t want = ((uint64_t)tile << 13) + ((uint64_t)lr << 7);       // lr == 64 carries into the tile bits
     int64_t lo = 0, hi = m;
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys2[mid] < want) lo = mid + 1; else hi = mid; }
     if (tile < ntiles) {

@@ -355,6 +355,45 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int32_t* __restrict__ i
   }
 }
 
+// Narrow blocks (ncols <= 4: the single vectors and K-column blocks of compute_hess, reference :157,:161): the
+// lanes-own-columns mapping above would leave 28+ of 32 lanes idle.  Here the lanes stride the ENTRIES of the row
+// (coalesced index / value streams, 4 independent chunks in flight) and one shuffle reduction per row finishes it.
+template <int NC>
+__global__ void __launch_bounds__(256) spmv_narrow_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                          const double* __restrict__ data, const double* __restrict__ X,
+                                                          int row_begin, int row_end, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps) {
+    const int b = indptr[row], e = indptr[row + 1];
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0.0;
+    for (int p0 = b + lane; p0 < e; p0 += 128) {
+      int col[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = p0 + 32 * u;
+        col[u] = p < e ? __ldcs(indices + p) : -1;
+        v[u] = p < e ? __ldcs(data + p) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (col[u] < 0) continue;
+        const double* xr = X + (int64_t)col[u] * NC;
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[c] += v[u] * xr[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const double s2 = warp_sum(acc[c]);
+      if (lane == 0) out[(int64_t)row * NC + c] = s2;
+    }
+  }
+}
+
 // SpMM + column quadratic forms for G matrices that share ONE sparsity pattern (e.g. IBD and its Hadamard
 // square): index stream and the gathered X rows - the dominant traffic, ncols*8 bytes per nonzero - are read
 // once for all G.  dots[g][c] = sum_i X[i,c] (A_g X)[i,c]; optionally (A_g X)[:, store_from:] is written out
@@ -1047,6 +1086,17 @@ static int spmm_impl(slmm_matset_t* ms, int32_t k, const double* d_X, int32_t nc
   const CsrDev& c = ms->m[k];
   if (!c.data) throw std::invalid_argument("matrix not set");
   const int grid = he_grid(r1 - r0);
+  if (!dot && ncols <= 4) {
+    switch (ncols) {
+      case 1: spmv_narrow_kernel<1><<<grid, 256>>>(c.indptr, c.indices, c.data, d_X, r0, r1, d_out); break;
+      case 2: spmv_narrow_kernel<2><<<grid, 256>>>(c.indptr, c.indices, c.data, d_X, r0, r1, d_out); break;
+      case 3: spmv_narrow_kernel<3><<<grid, 256>>>(c.indptr, c.indices, c.data, d_X, r0, r1, d_out); break;
+      default: spmv_narrow_kernel<4><<<grid, 256>>>(c.indptr, c.indices, c.data, d_X, r0, r1, d_out); break;
+    }
+    g_launch_count++;
+    CUDA_OK(cudaGetLastError());
+    return SLMM_OK;
+  }
   double* part = dot ? ms->partial((size_t)grid * ncols) : nullptr;
   const int cpl = (ncols + 31) / 32;
 #define SPMM_CASE(C)                                                                                                  \

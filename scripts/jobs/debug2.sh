@@ -15,6 +15,6 @@ for tid in ids:
     print(tid.split("::")[-1], "rc", r.returncode, tail, flush=True)
 PY
 echo "== tiled quadform test with device asserts"
-SLMM_TMA=0 timeout 300 python -m pytest tests/test_gpu_surface.py -m gpu -x -q -k "tiled and c1mini" > gpurun_out/dbg_tiled2.log 2>&1
+SLMM_TMA=0 timeout 300 python -m pytest tests/test_gpu_surface.py -m gpu -x -q -k "tiled" > gpurun_out/dbg_tiled2.log 2>&1
 grep -i "assert\|Assertion" gpurun_out/dbg_tiled2.log | sort | uniq -c | head -20
 tail -5 gpurun_out/dbg_tiled2.log

@@ -504,6 +504,13 @@ def test_pedigree_scale_factor_vs_oracle_panels(slmm, eng):
     (513, 259, 96, 802, 802, 1, 0, 0, 2),
     (736, 236, 64, 800, 800, 64, 64, 1 | 2 | 4, 1),  # lower-masked accumulate-negate: the in-block update of a narrow front
     (700, 700, 300, 1000, 1000, 301, 301, 1 | 4, 1),  # Schur complement of a front with an odd number of columns
+    (512, 384, 256, 802, 802, 0, 0, 0, 1),          # column stride not a multiple of 32 bytes
+    (512, 384, 256, 1000, 1000, 0, 0, 0, 1),        # ... of 128 bytes
+    (513, 259, 256, 800, 800, 0, 0, 0, 1),          # ragged edges, aligned
+    (513, 259, 256, 800, 800, 1, 0, 0, 1),          # ragged edges + odd start
+    (512, 384, 96, 800, 800, 0, 0, 0, 1),           # K = one pass of the stage ring
+    (512, 384, 300, 800, 800, 0, 0, 0, 1),          # ragged K
+    (513, 259, 96, 802, 802, 0, 0, 0, 1),
 ])
 def test_dmma_gemm_tiles_strided_multi_op(eng, M, N, K, lda, ldb, offa, offb, flags, copies):
     """The tile GEMMs (TMA-staged and cp.async-staged) on panel-shaped operands: explicit leading dimensions, odd base
