@@ -55,7 +55,7 @@ def emit(obj):
 
 # removal fractions found once by simulate_pedigree's bisection (seed 0); avoids repeating the search
 REMOVE_FRAC = {(250000, 1e-3): 0.065625, (100000, 1e-3): 0.084375, (20000, 1e-3): None,
-               (1000000, 1e-4): 0.103125}
+               (1000000, 1e-4): 0.103125, (3000000, 3.3e-5): 0.1125}
 
 
 def log(*a):

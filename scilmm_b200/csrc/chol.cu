@@ -473,8 +473,14 @@ struct PhaseBuilder {
       int64_t tiles = 0;
       double lf = 0;
       for (GemmOp& op : v) {
-        op.tiles_m = (op.M + T - 1) / T;
-        op.tiles_n = (op.N + T - 1) / T;
+        int em = 0, en = 0;
+        if (pass == 0) {      // TMA operands that start on an odd element: map based one element early, tile grid shifted
+          em = (int)(((uintptr_t)op.A >> 3) & 1);
+          en = (int)(((uintptr_t)op.B >> 3) & 1);
+          op.pad = em | (en << 1);
+        }
+        op.tiles_m = (op.M + em + T - 1) / T;
+        op.tiles_n = (op.N + en + T - 1) / T;
         op.tile_start = (int32_t)tiles;
         tiles += (int64_t)op.tiles_m * op.tiles_n;
         double f = 2.0 * op.M * op.N * op.K;
@@ -496,8 +502,7 @@ struct PhaseBuilder {
         // tensor maps of the two operands: base rounded down to 16 bytes (op.pad bit 0 / 1 = the operand starts one
         // element after its map's base), extents = the op's own M / N x K so that ragged edges are zero-filled
         for (GemmOp& op : v) {
-          const int sa = (int)(((uintptr_t)op.A >> 3) & 1), sb = (int)(((uintptr_t)op.B >> 3) & 1);
-          op.pad = sa | (sb << 1);
+          const int sa = op.pad & 1, sb = (op.pad >> 1) & 1;
           sch.tmaps.push_back(encode_tmap(op.A - sa, (uint64_t)op.M + sa, (uint64_t)op.K, (uint64_t)op.a_sk));
           sch.tmaps.push_back(encode_tmap(op.B - sb, (uint64_t)op.N + sb, (uint64_t)op.K, (uint64_t)op.b_sk));
         }

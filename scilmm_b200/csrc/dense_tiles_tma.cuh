@@ -15,6 +15,12 @@
 // physical rows {0,1,8,9,2,3,10,11} (+4 for the second 8-row group): within a half-warp the chunks are {c, c^4} and
 // the XOR with k only permutes the low two chunk bits - conflict free.  The same permutation is applied to the
 // fragment columns (B) and undone in the epilogue's C indexing, so it is invisible outside the kernel.
+//
+// Alignment: a bulk tensor copy must start on a 16-byte boundary (an odd element offset in the contiguous dimension
+// raises an illegal-instruction fault), but panel blocks start at row ns or c1, which may be odd.  The tensor map of
+// such an operand is based one element EARLIER (aligned) and the op's tile grid is shifted with it: tile row i'
+// stands for row i' - 1 of the op (op.pad bit 0 for A, bit 1 for B), the extra leading row / column is masked in the
+// epilogue.  Shared-memory addressing is the same for aligned and shifted operands.
 #pragma once
 #include <cuda.h>
 
@@ -61,7 +67,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemm_tiles_tma_kernel(const Ge
   const int tiles_m = op.tiles_m;
   const int tm0 = (local % tiles_m) * TM, tn0 = (local / tiles_m) * TN;
   const int flags = op.flags;
-  if ((flags & GF_LOWER) && tm0 + TM <= tn0) return;
+  const int sa = op.pad & 1, sb = (op.pad >> 1) & 1;           // tile rows / columns are offset by one element
+  if ((flags & GF_LOWER) && tm0 + TM - 1 - sa < tn0 - sb) return;   // tile entirely above the diagonal
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = op.M, N = op.N, K = op.K;
@@ -78,27 +85,28 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemm_tiles_tma_kernel(const Ge
     const int pw = warp - NCW;
     if ((flags & GF_ACCUM) && op.c_si == 1) {                    // pull the C tile into L2 under the main loop
       const int pt = pw * 32 + lane;
-      if (pt < TN && tn0 + pt < N) {
-        const double* ccol = op.C + (int64_t)tm0 + (int64_t)(tn0 + pt) * op.c_sj;
-        const int rows = min(TM, M - tm0);
-        const int r_first = (flags & GF_LOWER) ? max(0, tn0 + pt - tm0) : 0;
+      const int j = tn0 + pt - sb, i0 = max(0, tm0 - sa);
+      if (pt < TN && j >= 0 && j < N) {
+        const double* ccol = op.C + (int64_t)i0 + (int64_t)j * op.c_sj;
+        const int rows = min(TM, M - i0);
+        const int r_first = (flags & GF_LOWER) ? max(0, j - i0) : 0;
         for (int r = (r_first / 16) * 16; r < rows; r += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ccol + r));
       }
     }
     if (pw == 0 && lane == 0) {
       const CUtensorMap* mapA = maps + 2 * (int64_t)opi;
       const CUtensorMap* mapB = mapA + 1;
-      const int a_r = tm0 + (op.pad & 1), b_r = tn0 + ((op.pad >> 1) & 1);   // operands start 0 or 1 element after the map's base
+      const int a_r = tm0, b_r = tn0;       // always even: the maps of odd-offset operands are based one element early
       for (int s = 0; s < nslab; s++) {
         const int stage = s % STAGES, use = s / STAGES;
         if (use > 0) mbar_wait(empty_bar + stage, (use - 1) & 1);
         mbar_expect_tx(full_bar + stage, TMA_STAGE_BYTES);
-        const uint32_t sa = base + stage * TMA_STAGE_BYTES, sb = sa + TMA_OPERAND_BYTES;
+        const uint32_t dst_a = base + stage * TMA_STAGE_BYTES, dst_b = dst_a + TMA_OPERAND_BYTES;
         const int k0 = s * KS;
 #pragma unroll
-        for (int b = 0; b < 8; b++) tma_load_2d(sa + b * TMA_BOX_BYTES, mapA, a_r + 16 * b, k0, full_bar + stage);
+        for (int b = 0; b < 8; b++) tma_load_2d(dst_a + b * TMA_BOX_BYTES, mapA, a_r + 16 * b, k0, full_bar + stage);
 #pragma unroll
-        for (int b = 0; b < 8; b++) tma_load_2d(sb + b * TMA_BOX_BYTES, mapB, b_r + 16 * b, k0, full_bar + stage);
+        for (int b = 0; b < 8; b++) tma_load_2d(dst_b + b * TMA_BOX_BYTES, mapB, b_r + 16 * b, k0, full_bar + stage);
       }
     }
     return;
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemm_tiles_tma_kernel(const Ge
   const int64_t c_si = op.c_si, c_sj = op.c_sj;
 #pragma unroll
   for (int mi = 0; mi < MI; mi++) {
-    const int i = tm0 + wm0 + 16 * (mi >> 1) + 4 * (mi & 1) + colg;
+    const int i = tm0 + wm0 + 16 * (mi >> 1) + 4 * (mi & 1) + colg - sa;
     double old[NI][2];
     bool ok[NI][2];
     int jj[NI][2];
@@ -161,9 +169,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemm_tiles_tma_kernel(const Ge
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int q = 2 * t + h;                                  // logical column 0..7 of the 8-column group
-        const int j = tn0 + wn0 + 16 * (ni >> 1) + 4 * (ni & 1) + (q & 1) + ((q >> 1) & 1) * 8 + (q >> 2) * 2;
+        const int j = tn0 + wn0 + 16 * (ni >> 1) + 4 * (ni & 1) + (q & 1) + ((q >> 1) & 1) * 8 + (q >> 2) * 2 - sb;
         jj[ni][h] = j;
-        ok[ni][h] = (i < M) && (j < N) && !(lower && i < j);
+        ok[ni][h] = (i >= 0) && (i < M) && (j >= 0) && (j < N) && !(lower && i < j);
         old[ni][h] = 0.0;
       }
     if (accum) {
