@@ -6,7 +6,8 @@
 #include <stdint.h>
 
 /* child update matrix U (rs x rs column-major, lower triangle valid) is added into the parent front:
- * columns with rel < ns go to the parent's panel (ms x ns, ld = ms), the rest to its update matrix
+ * columns with rel < ns go to the parent's panel (ns columns, leading dimension ms - the engine pads it to an even
+ * number of rows), the rest to its update matrix
  * (rsp x rsp, ld = rsp).  Lower triangle only. */
 void oracle_extend_add(const double* U, int64_t rs, const int32_t* rel, double* panel, int64_t ms, int64_t ns,
                        double* Up, int64_t rsp) {

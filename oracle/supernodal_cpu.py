@@ -131,7 +131,7 @@ class SupernodalCPUFactor(object):
                         continue
                     nsc = first[c + 1] - first[c]
                     rel = rel_all[rowptr[c] + nsc:rowptr[c + 1]]
-                    lib.oracle_extend_add(_p(Uc), Uc.shape[0], _p(rel), _p(panel), ms, ns,
+                    lib.oracle_extend_add(_p(Uc), Uc.shape[0], _p(rel), _p(panel), int(a['sn_ld'][s]), ns,
                                           _p(Up) if rs else None, rs)
                 if ns == 1:
                     d = panel[0, 0]

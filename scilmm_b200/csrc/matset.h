@@ -44,11 +44,16 @@ struct QuadTiles {
   int32_t* dcols = nullptr;         // [ndistinct] ORIGINAL row id of the gathered block for every tile column
   int32_t* rowid = nullptr;         // [nrb*64] original row id of every permuted row (-1 past n)
   int32_t* cta_begin = nullptr;     // [ncta+1] contiguous tile ranges of equal cost
+  int32_t* pair_base = nullptr;     // [ncta+1] first (CTA, row block) pair of every CTA
+  int32_t* pair_rb = nullptr;       // [npairs] row block of every pair
+  double* hpairs = nullptr;         // [npairs][64][2][16] narrow-block row products, one block per pair
+  int npairs = 0;
   std::vector<double*> vals;        // per matrix of the set sharing this pattern: weighted values in tile order
   std::vector<int> vals_of;         // which matrix each vals[] belongs to
   void release() {
     dev_free(tile_ptr); dev_free(tile_rb); dev_free(tile_dc0); dev_free(tile_nc); dev_free(rowptr); dev_free(rc);
-    dev_free(pos); dev_free(dcols); dev_free(rowid); dev_free(cta_begin);
+    dev_free(pos); dev_free(dcols); dev_free(rowid); dev_free(cta_begin); dev_free(pair_base); dev_free(pair_rb); dev_free(hpairs);
+    pair_base = pair_rb = nullptr; hpairs = nullptr; npairs = 0;
     for (double* v : vals) dev_free(v);
     vals.clear(); vals_of.clear();
     tile_ptr = nullptr; tile_rb = tile_dc0 = tile_nc = dcols = rowid = cta_begin = nullptr; rowptr = rc = nullptr; pos = nullptr;

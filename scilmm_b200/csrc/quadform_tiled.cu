@@ -9,7 +9,10 @@
 // lower triangle is cut into tiles of 64 permuted rows x 64 DISTINCT columns; a CTA stages the 64 gathered rows of the
 // dense block in shared memory once and every entry of the tile reads them from there:
 //   dots[g][c] = sum_i x[i,c] * ( sum_j v_g(i,j) x[j,c] ),  v = a for the diagonal, 2a below it (symmetric matrix);
-//   Mh[g]      = sum_i xb_i (sum_j v_g(i,j) xb_j)'  for the first nb columns (the narrow block), Gram = (Mh + Mh')/2.
+//   Mh[g]      = sum_i xb_i (sum_j v_g(i,j) xb_j)'  for the first nb columns (the narrow block), Gram = (Mh + Mh')/2:
+//                the pass leaves the row products hb_i = sum_j v(i,j) xb_j per (CTA, row block) pair in global memory
+//                and a small second kernel folds the outer products (a serial fold inside the pass cost 34 of 40 ms:
+//                the tree's leaves give some CTAs hundreds of tiny row blocks).
 // Everything is accumulated in a fixed order (tiles are assigned to CTAs by a static partition, rows to warps by
 // index): results are bit-reproducible.  The tiling is built once per session on the device (two radix sorts).
 #include <algorithm>
@@ -135,7 +138,8 @@ struct QtArgs {
   int64_t nentries, ndistinct;
   int32_t ntiles, nrb, n, pad;
   const int64_t* tile_ptr;
-  const int32_t *tile_rb, *tile_dc0, *tile_nc, *dcols, *rowid, *cta_begin;
+  const int32_t *tile_rb, *tile_dc0, *tile_nc, *dcols, *rowid, *cta_begin, *pair_base;
+  double* hpairs;
   const uint16_t *rowptr, *rc;
   const double* vals[2];
 };
@@ -152,7 +156,6 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   extern __shared__ double qsm[];
   double* Xs = qsm;                                   // [QT_CH][LDX]  gathered rows of the dense block
   double* hbS = Xs + QT_CH * LDX;                     // [QT_RB][G][QT_NB]  narrow-block row products of this row block
-  double* MhS = hbS + QT_RB * G * QT_NB;              // [G][QT_NB][QT_NB]
   __shared__ uint16_t rp_s[QT_RB + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_begin = a.cta_begin[blockIdx.x], t_end = a.cta_begin[blockIdx.x + 1];
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   for (int g = 0; g < G; g++)
 #pragma unroll
     for (int c = 0; c < CPL; c++) dot[g][c] = 0.0;
-  for (int q = tid; q < QT_CH * LDX + QT_RB * G * QT_NB + G * QT_NB * QT_NB; q += 256) qsm[q] = 0.0;   // incl. the padding columns of Xs
+  for (int q = tid; q < QT_CH * LDX + QT_RB * G * QT_NB; q += 256) qsm[q] = 0.0;   // incl. the padding columns of Xs
+  int pair = a.pair_base[blockIdx.x];
   __syncthreads();
   assert(t_begin >= 0 && t_begin <= t_end && t_end <= a.ntiles);
   for (int t = t_begin; t < t_end; t++) {
@@ -225,31 +229,16 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
       }
     }
     __syncthreads();
-    // end of the row block (or of this CTA's range): fold the narrow-block products into Mh (one warp, fixed order)
+    // end of the row block (or of this CTA's range): park the narrow-block row products of this (CTA, row block)
+    // pair in global memory; qt_gram_finish_kernel folds them into the Gram matrix
     if (nb > 0 && (t + 1 == t_end || a.tile_rb[t + 1] != rb)) {
-      if (warp == 0) {
-        for (int lr = 0; lr < QT_RB; lr++) {
-          const int row = a.rowid[rb * QT_RB + lr];
-          if (row < 0) break;
-          const double bi = lane < nb ? X[(int64_t)row * ncx + lane] : 0.0;
-          double hb[G];
-#pragma unroll
-          for (int g = 0; g < G; g++) hb[g] = lane < nb ? hbS[(lr * G + g) * QT_NB + lane] : 0.0;
-          for (int p = 0; p < nb; p++) {
-            const double bp = __shfl_sync(0xffffffffu, bi, p);
-            if (lane < nb) {
-#pragma unroll
-              for (int g = 0; g < G; g++) MhS[(g * QT_NB + p) * QT_NB + lane] += bp * hb[g];
-            }
-          }
-        }
-      }
-      __syncthreads();
-      for (int q = tid; q < QT_RB * G * QT_NB; q += 256) hbS[q] = 0.0;
+      double* hp = a.hpairs + (int64_t)pair * (QT_RB * 2 * QT_NB);
+      for (int q = tid; q < QT_RB * G * QT_NB; q += 256) { hp[q] = hbS[q]; hbS[q] = 0.0; }
+      pair++;
       __syncthreads();
     }
   }
-  // per-CTA partials: dots over the 8 warps (fixed order), Mh as it stands (x 1/2: Gram = half + half')
+  // per-CTA partials: dots over the 8 warps (fixed order)
   double* red = Xs;                                    // [8][G][LDX]
   __syncthreads();
 #pragma unroll
@@ -263,11 +252,53 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     for (int w = 0; w < 8; w++) s += red[(w * G + g) * LDX + j];
     part_dots[(int64_t)blockIdx.x * G * ncx + q] = s;
   }
-  if (nb > 0)
-    for (int q = tid; q < G * nb * nb; q += 256) {
-      const int g = q / (nb * nb), p = (q / nb) % nb, j = q % nb;
-      part_gram[(int64_t)blockIdx.x * G * nb * nb + q] = 0.5 * MhS[(g * QT_NB + p) * QT_NB + j];
+}
+
+// Gram fold: Mh[g] += xb_i hb_i' over the rows of every (CTA, row block) pair.  CTA c takes pairs c, c + gridDim, ...
+// (a fixed assignment), warp w the rows w, w + 8, ...; lane q < nb owns column q of Mh in registers.
+template <int G>
+__global__ void __launch_bounds__(256) qt_gram_finish_kernel(const double* __restrict__ hpairs, const int32_t* __restrict__ pair_rb,
+                                                             int npairs, const int32_t* __restrict__ rowid,
+                                                             const double* __restrict__ X, int ncx, int nb,
+                                                             double* __restrict__ part_gram) {
+  __shared__ double red[8][G][QT_NB][QT_NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double mh[G][QT_NB];
+#pragma unroll
+  for (int g = 0; g < G; g++)
+#pragma unroll
+    for (int p = 0; p < QT_NB; p++) mh[g][p] = 0.0;
+  for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+    const int rb = pair_rb[pr];
+    const double* hp = hpairs + (int64_t)pr * (QT_RB * 2 * QT_NB);
+    for (int lr = warp; lr < QT_RB; lr += 8) {
+      const int row = rowid[rb * QT_RB + lr];
+      if (row < 0) continue;
+      const double bi = lane < nb ? X[(int64_t)row * ncx + lane] : 0.0;
+      double hb[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) hb[g] = lane < nb ? hp[(lr * G + g) * QT_NB + lane] : 0.0;
+#pragma unroll
+      for (int p = 0; p < QT_NB; p++) {
+        const double bp = __shfl_sync(0xffffffffu, bi, p);      // 0 for p >= nb
+#pragma unroll
+        for (int g = 0; g < G; g++) mh[g][p] += bp * hb[g];
+      }
     }
+  }
+  if (lane < QT_NB) {
+#pragma unroll
+    for (int g = 0; g < G; g++)
+#pragma unroll
+      for (int p = 0; p < QT_NB; p++) red[warp][g][p][lane] = mh[g][p];
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < G * nb * nb; q += 256) {
+    const int g = q / (nb * nb), p = (q / nb) % nb, j = q % nb;
+    double s2 = 0.0;
+    for (int w = 0; w < 8; w++) s2 += red[w][g][p][j];
+    part_gram[(int64_t)blockIdx.x * G * nb * nb + q] = 0.5 * s2;        // Gram = half + half'
+  }
 }
 
 __global__ void qt_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ dst) {
@@ -287,7 +318,7 @@ __global__ void qt_reduce_kernel(const double* __restrict__ partial, int nblocks
 template <int CPL, int G>
 static void qt_launch(const QuadTiles& T, const QtArgs& a, const double* d_X, int ncx, int nb, double* part_dots,
                       double* part_gram, double* d_dots, double* d_gram) {
-  const size_t smem = ((size_t)QT_CH * CPL * 32 + (size_t)QT_RB * G * QT_NB + (size_t)G * QT_NB * QT_NB) * sizeof(double);
+  const size_t smem = ((size_t)QT_CH * CPL * 32 + (size_t)QT_RB * G * QT_NB) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_OK(cudaFuncSetAttribute(quadform_tiled_kernel<CPL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -297,8 +328,10 @@ static void qt_launch(const QuadTiles& T, const QtArgs& a, const double* d_X, in
   qt_reduce_kernel<<<G * ncx, 256>>>(part_dots, T.ncta, G * ncx, d_dots);
   g_launch_count += 2;
   if (nb > 0) {
-    qt_reduce_kernel<<<G * nb * nb, 256>>>(part_gram, T.ncta, G * nb * nb, d_gram);
-    g_launch_count++;
+    const int gf = std::max(1, std::min(T.npairs, 148 * 4));
+    qt_gram_finish_kernel<G><<<gf, 256>>>(T.hpairs, T.pair_rb, T.npairs, T.rowid, d_X, ncx, nb, part_gram);
+    qt_reduce_kernel<<<G * nb * nb, 256>>>(part_gram, gf, G * nb * nb, d_gram);
+    g_launch_count += 2;
   }
 }
 
@@ -426,6 +459,18 @@ int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm,
       for (int q = cta + 1; q <= ncta; q++) cta_begin[q] = ntiles;
     }
     T.cta_begin = dev_upload(cta_begin.data(), cta_begin.size());
+    // (CTA, row block) pairs: where each CTA parks the narrow-block row products of the row blocks it touches
+    std::vector<int32_t> pair_base(ncta + 1, 0), pair_rb;
+    for (int c2 = 0; c2 < ncta; c2++) {
+      pair_base[c2] = (int32_t)pair_rb.size();
+      for (int t = cta_begin[c2]; t < cta_begin[c2 + 1]; t++)
+        if (t == cta_begin[c2] || tile_rb[t] != tile_rb[t - 1]) pair_rb.push_back(tile_rb[t]);
+    }
+    pair_base[ncta] = (int32_t)pair_rb.size();
+    T.npairs = (int)pair_rb.size();
+    T.pair_base = dev_upload(pair_base.data(), pair_base.size());
+    T.pair_rb = dev_upload(pair_rb.data(), pair_rb.size());
+    T.hpairs = dev_alloc<double>((size_t)T.npairs * QT_RB * 2 * QT_NB);
     T.ntiles = ntiles; T.nrb = nrb; T.ncta = ncta; T.nentries = m; T.ndistinct = ndist;
     CUDA_OK(cudaDeviceSynchronize());
   }
@@ -466,6 +511,7 @@ int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
   a.nentries = T.nentries; a.ndistinct = T.ndistinct; a.ntiles = T.ntiles; a.nrb = T.nrb; a.n = ms->n; a.pad = 0;
   a.tile_ptr = T.tile_ptr; a.tile_rb = T.tile_rb; a.tile_dc0 = T.tile_dc0; a.tile_nc = T.tile_nc; a.dcols = T.dcols;
   a.rowid = T.rowid; a.cta_begin = T.cta_begin; a.rowptr = T.rowptr; a.rc = T.rc;
+  a.pair_base = T.pair_base; a.hpairs = T.hpairs;
   for (int g = 0; g < nk; g++) {
     a.vals[g] = nullptr;
     for (size_t q = 0; q < T.vals_of.size(); q++)
@@ -473,7 +519,7 @@ int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
     if (!a.vals[g]) throw std::invalid_argument("matrix has no tiled values (slmm_matset_build_tiles per matrix)");
   }
   if (nk == 1) a.vals[1] = a.vals[0];
-  const size_t np = (size_t)T.ncta * nk * ncols, ng = (size_t)T.ncta * nk * nb * nb;
+  const size_t np = (size_t)T.ncta * nk * ncols, ng = (size_t)std::max(1, std::min(T.npairs, 148 * 4)) * nk * nb * nb;
   double* part = ms->partial(np + ng);
   const int cpl = (ncols + 31) / 32;
 #define QT_CASE(C)                                                                                             \

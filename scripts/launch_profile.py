@@ -11,17 +11,17 @@ A, T, D, F = P.numerator(ped["rel"]); keep, (A,) = P.drop_unrelated(A); nn = A.s
 mats = [A, P.epistasis(A), sp.eye(nn).tocsr()]
 rng = np.random.default_rng(1); cov = np.hstack([rng.standard_normal((nn, 10)), np.ones((nn, 1))]); y = rng.standard_normal(nn)
 chol = S.SparseCholesky(rng="device"); ses = chol._session(mats, cov, y); sig = np.array([0.3, 0.15, 0.55])
-names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big", "init_w", "reduce", "-", "-", "skinny_f1", "skinny_f2"]
+names = ["potrf", "gemm_big", "gemm_small", "extend_add", "rhs_pull", "extend_add_big", "init_w", "reduce", "-", "-", "skinny_f1", "skinny_f2", "gemm_tma"]
 def report(tag):
     ms, fl, kind, grid = ses.eng.launch_profile()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.savez(os.path.join(ROOT, "gpurun_out", "launches_%s.npz" % tag.split()[0]), ms=ms, fl=fl, kind=kind, grid=grid)
     print("==", tag, "launches", ms.size, "total %.1f ms" % ms.sum())
-    for k in range(12):
+    for k in range(13):
         m = kind == k
         if m.sum() == 0: continue
         print("  %-10s n=%5d  %.1f ms  %.2f TFLOP/s" % (names[k], m.sum(), ms[m].sum(), fl[m].sum() / max(ms[m].sum(), 1e-9) / 1e9))
-    for k in (1, 2):
+    for k in (1, 2, 12):
         m = kind == k
         if m.sum() == 0: continue
         rate = fl[m] / np.maximum(ms[m], 1e-6) / 1e9

@@ -205,3 +205,22 @@ def test_entry_map_triangle_rules(golden_small):
         Lx[tgt[ok]] = pat.data[ok]
         panels.append(Lx)
     assert np.array_equal(panels[0], panels[1]) and np.array_equal(panels[0], panels[2])
+
+
+@pytest.mark.parametrize("case,tag", [("golden_small", "k4"), ("golden_c1mini", "k4")])
+def test_cpu_supernodal_oracle_on_the_engine_plan(case, tag, request):
+    """oracle/supernodal_cpu.py on the ENGINE's plan (padded panels, relaxed supernodes: the layout the panel-by-panel
+    GPU comparison uses) against dense LAPACK: factor, logdet, solves, L*Z."""
+    from oracle.cpu_factor import DenseFactor
+    from oracle.supernodal_cpu import SupernodalCPUFactor, SupernodalPlan
+    g = request.getfixturevalue(case)
+    V = g.csc("V_" + tag)
+    plan = SupernodalPlan(sp.csr_matrix((V.data, V.indices, V.indptr), shape=V.shape))
+    assert np.any(plan.a["sn_ld"] != plan.a["sn_nrow"])        # some panel is padded
+    f = SupernodalCPUFactor(V, plan=plan)
+    d = DenseFactor(V, plan.a["perm"])
+    b = np.random.default_rng(0).standard_normal((g.n, 4))
+    assert abs(f.logdet() - d.logdet()) < 1e-12 * abs(d.logdet())
+    assert np.max(np.abs(f(b) - d(b))) < 1e-11 * np.max(np.abs(d(b)))
+    assert abs(f.L() - d.L()).max() < 1e-12
+    assert np.max(np.abs(f.lmul_unperm(b) - d.L().dot(b)[np.argsort(d.P())])) < 1e-11
