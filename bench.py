@@ -55,7 +55,8 @@ def emit(obj):
 
 # removal fractions found once by simulate_pedigree's bisection (seed 0); avoids repeating the search
 REMOVE_FRAC = {(250000, 1e-3): 0.065625, (100000, 1e-3): 0.084375, (20000, 1e-3): None,
-               (1000000, 1e-4): 0.103125, (3000000, 3.3e-5): 0.1125}
+               (1000000, 1e-4): 0.103125, (3000000, 3.3e-5): 0.1125,
+               (3000000, 1e-5): 0.16875, (3000000, 2e-5): 0.13125}
 
 
 def log(*a):
@@ -391,7 +392,20 @@ def main():
     t_solve_narrow = ev(lambda: ses.eng.solve_(Bn.clone()))
     Xq = torch.randn(n, s + 1, dtype=torch.float64, device="cuda")
     groups = ses.matset.pattern_groups(2)
-    t_quad = ev(lambda: [ses.matset.quadform_multi(ks, Xq) for ks in groups])
+    nbq = cov.shape[1] + 1
+    Bq = torch.randn(n, nbq, dtype=torch.float64, device="cuda")
+
+    def quadforms(W):
+        """the quadratic-form / Gram pass of one evaluation: tiled kernel where the session built tiles"""
+        out = []
+        for ks in groups:
+            if ses.use_tiles and ses.matset.has_tiles(ks) and nbq + W.shape[1] <= 160:
+                out.append(ses.matset.quadform_tiled(ks, torch.cat([Bq, W], dim=1), nbq))
+            else:
+                out.append(ses.matset.quadform_gram_multi(ks, W, Bq))
+        return out
+    t_quad = ev(lambda: quadforms(Bs))
+    t_quad_rowwise = ev(lambda: [ses.matset.quadform_multi(ks, Xq) for ks in groups])
     # the C3 "AI-REML iteration" of SURVEY 8d = one evaluation + compute_hess (reference :147-168)
     t_hess = ev(lambda: S._hess_device(ses, ses.eng), reps=1)
     # the phase that shards across ranks: this rank's probe columns through L*Z, the solve and the quadratic forms;
@@ -400,9 +414,7 @@ def main():
     Bloc = Bs[:, lo_c:hi_c].contiguous()
 
     def probe_pipeline(Bp):
-        W = ses.eng.solve_(ses.eng.lmul(Bp))
-        X = torch.cat([W, W[:, :1]], dim=1).contiguous()
-        return [ses.matset.quadform_multi(ks, X) for ks in groups]
+        return quadforms(ses.eng.solve_(ses.eng.lmul(Bp)))
     t_shard_local = max_over_ranks(ev(lambda: probe_pipeline(Bloc)))
     t_shard_full = ev(lambda: probe_pipeline(Bs)) if world > 1 else t_shard_local
     # profiled pass: per-kernel-kind device time with events around every launch
@@ -442,10 +454,13 @@ def main():
     half = [(z + n) / 2.0 for z in nnzs]
     quad_bytes = 12.0 * half[0] + 4 * (n + 1) + 8.0 * half[1] + 12.0 * half[2] + 4 * (n + 1) + 2 * 8.0 * n * (s + 1)
     quad_gather_bytes = (half[0] + half[2]) * 8.0 * (s + 1)
+    # SURVEY 8d figure for the pass: 12 nnz + 4(n+1) per pattern, 8 nnz for a matrix sharing a pattern, the dense
+    # block [narrow | probes] read once per pattern group
+    quad_bytes_survey = 12.0 * nnzs[0] + 8.0 * nnzs[1] + 12.0 * nnzs[2] + 2 * 4 * (n + 1) + 2 * 8.0 * n * (s + nbq)
     solve_flops = 4.0 * st["nnzL"] * s
     phases = {
         "assemble_ms": round(t_asm, 3), "factorize_ms": round(t_fac, 2), "solve128_ms": round(t_solve, 2),
-        "lmul128_ms": round(t_lmul, 2), "quadforms_ms": round(t_quad, 2),
+        "lmul128_ms": round(t_lmul, 2), "quadforms_ms": round(t_quad, 2), "quadforms_rowwise_kernel_ms": round(t_quad_rowwise, 2),
         "solve_narrow_ms": round(t_solve_narrow, 2), "solve_narrow_cols": int(cov.shape[1] + 1),
         "solve_narrow_gbs": round((2.0 * 8.0 * st["lsize"]) / t_solve_narrow / 1e6, 1),
         "solve128_tflops": round(solve_flops / t_solve / 1e9, 2),
@@ -459,6 +474,8 @@ def main():
         "cholesky_issued_gflops": round(st["issued_flops"] / t_fac / 1e6, 1),
         "solve_gbs": round(solve_bytes / t_solve / 1e6, 1), "quadforms_gbs": round(quad_bytes / t_quad / 1e6, 1),
         "quadforms_gather_gbs": round(quad_gather_bytes / t_quad / 1e6, 1),
+        "quadforms_survey_bytes_gbs": round(quad_bytes_survey / t_quad / 1e6, 1),
+        "quadforms_frac_of_hbm": round(quad_bytes_survey / t_quad / 1e6 / hbm, 3),
         "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src,
         "profile_ms": {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]},
     }

@@ -44,9 +44,28 @@ __global__ void __launch_bounds__(SK_F1_COLS) skinny_f1_kernel(const GemmOp* __r
   for (int k0 = 0; k0 < kend; k0 += SK_F1_KC) {
     const int kc = min(SK_F1_KC, kend - k0);
     __syncthreads();
-    for (int q = threadIdx.x; q < kc * MT; q += SK_F1_COLS) {
-      const int k = q / MT, i = q - k * MT;
-      As[q] = i < M ? op.A[(int64_t)i + (int64_t)(k0 + k) * op.a_sk] : 0.0;
+    {
+      // stage A(0..M, k0..k0+kc) as [k][MT]: coalesced along the M values of one k (contiguous in the RHS block), four
+      // independent loads in flight per thread (a load-store loop per element cost ~1 us of latency per trip)
+      const int total = kc * M;
+      const double* __restrict__ Ab = op.A + (int64_t)k0 * op.a_sk;
+      const int64_t a_sk = op.a_sk;
+      for (int q0 = threadIdx.x; q0 < total; q0 += 4 * SK_F1_COLS) {
+        double v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int q = q0 + u * SK_F1_COLS;
+          const int k = q / M, i = q - k * M;
+          dst[u] = q < total ? k * MT + i : -1;
+          v[u] = q < total ? Ab[(int64_t)k * a_sk + i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (dst[u] >= 0) As[dst[u]] = v[u];
+      }
+      if (M < MT)
+        for (int q = threadIdx.x; q < kc * (MT - M); q += SK_F1_COLS) As[(q / (MT - M)) * MT + M + q % (MT - M)] = 0.0;
     }
     __syncthreads();
     if (!active) continue;
@@ -79,7 +98,7 @@ __global__ void __launch_bounds__(SK_F1_COLS) skinny_f1_kernel(const GemmOp* __r
 }
 
 template <int MT>
-__global__ void __launch_bounds__(256) skinny_f2_kernel(const GemmOp* __restrict__ ops,
+__global__ void __launch_bounds__(256, 2) skinny_f2_kernel(const GemmOp* __restrict__ ops,
                                                         const int32_t* __restrict__ tile_op) {
   extern __shared__ double As2[];                      // [i][K] (lanes read consecutive k: conflict free)
   const int tile = blockIdx.x;
@@ -88,49 +107,83 @@ __global__ void __launch_bounds__(256) skinny_f2_kernel(const GemmOp* __restrict
   const int M = op.M, N = op.N, K = op.K, flags = op.flags;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int32_t* __restrict__ kidx = op.a_kidx;
-  for (int q = threadIdx.x; q < K * MT; q += 256) {
-    const int i = q / K, k = q - i * K;
-    double v = 0.0;
-    if (i < M) v = op.A[(int64_t)i + (int64_t)(kidx ? kidx[k] : k) * op.a_sk];
-    As2[q] = v;
+  {
+    // stage A(0..M, 0..K) as [i][K] (lanes of the main loop read consecutive k): source walked with i fastest (the M
+    // values of one gathered row are contiguous), four independent loads in flight per thread
+    const int total = K * M;
+    const int64_t a_sk = op.a_sk;
+    for (int q0 = threadIdx.x; q0 < total; q0 += 4 * 256) {
+      double v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = q0 + u * 256;
+        const int k = q / M, i = q - k * M;
+        dst[u] = q < total ? i * K + k : -1;
+        v[u] = q < total ? op.A[(int64_t)i + (int64_t)(kidx ? kidx[k] : k) * a_sk] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (dst[u] >= 0) As2[dst[u]] = v[u];
+    }
+    for (int q = threadIdx.x + M * K; q < MT * K; q += 256) As2[q] = 0.0;
   }
   __syncthreads();
   const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG;
-  for (int jj = warp; jj < SK_F2_COLS; jj += 8) {
-    const int j = j0 + jj;
-    if (j >= N) break;
-    const double* __restrict__ Bj = op.B + (int64_t)j * op.b_sj;
-    double acc[MT];
+  // each warp owns columns warp, warp + 8, ...; two columns per trip with 4 + 4 independent coalesced loads in flight
+  for (int jj = warp; jj < SK_F2_COLS; jj += 16) {
+    const int j0c = j0 + jj, j1c = j0 + jj + 8;
+    if (j0c >= N) break;
+    const bool two = j1c < N && jj + 8 < SK_F2_COLS;
+    const double* __restrict__ B0 = op.B + (int64_t)j0c * op.b_sj;
+    const double* __restrict__ B1 = op.B + (int64_t)(two ? j1c : j0c) * op.b_sj;
+    double acc0[MT], acc1[MT];
 #pragma unroll
-    for (int i = 0; i < MT; i++) acc[i] = 0.0;
+    for (int i = 0; i < MT; i++) acc0[i] = acc1[i] = 0.0;
     int k = lane;
-    for (; k + 96 < K; k += 128) {                     // 4 independent coalesced loads in flight per lane
-      double b[4];
+    for (; k + 96 < K; k += 128) {
+      double b0[4], b1[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) b[u] = __ldcs(Bj + k + 32 * u);
+      for (int u = 0; u < 4; u++) { b0[u] = __ldcs(B0 + k + 32 * u); b1[u] = __ldcs(B1 + k + 32 * u); }
 #pragma unroll
       for (int u = 0; u < 4; u++)
 #pragma unroll
-        for (int i = 0; i < MT; i++) acc[i] += As2[i * K + k + 32 * u] * b[u];
+        for (int i = 0; i < MT; i++) {
+          const double a = As2[i * K + k + 32 * u];
+          acc0[i] += a * b0[u];
+          acc1[i] += a * b1[u];
+        }
     }
     for (; k < K; k += 32) {
-      const double b = __ldcs(Bj + k);
+      const double b0 = __ldcs(B0 + k), b1 = __ldcs(B1 + k);
 #pragma unroll
-      for (int i = 0; i < MT; i++) acc[i] += As2[i * K + k] * b;
+      for (int i = 0; i < MT; i++) {
+        const double a = As2[i * K + k];
+        acc0[i] += a * b0;
+        acc1[i] += a * b1;
+      }
     }
-    // reduce the MT accumulators over the warp; lane i ends up with row i
-    double mine = 0.0;
+    // reduce the accumulators over the warp; lane i ends up with row i
+    double m0 = 0.0, m1 = 0.0;
 #pragma unroll
     for (int i = 0; i < MT; i++) {
-      double v = acc[i];
+      double v0 = acc0[i], v1 = acc1[i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == i) mine = v;
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      if (lane == i) { m0 = v0; m1 = v1; }
     }
     if (lane < M) {
-      double* c = op.C + lane + (int64_t)j * op.c_sj;
-      const double v = neg ? -mine : mine;
-      *c = accum ? *c + v : v;
+      double* c0 = op.C + lane + (int64_t)j0c * op.c_sj;
+      const double v0 = neg ? -m0 : m0;
+      *c0 = accum ? *c0 + v0 : v0;
+      if (two) {
+        double* c1 = op.C + lane + (int64_t)j1c * op.c_sj;
+        const double v1 = neg ? -m1 : m1;
+        *c1 = accum ? *c1 + v1 : v1;
+      }
     }
   }
 }

@@ -1,0 +1,77 @@
+"""BASELINE config 5: simulated pedigree of 3,000,000 individuals - a Haseman-Elston fit with K = 3 (IBD, A o A,
+household) plus ONE sparse Cholesky factorization / logdet of V at fixed sigma: the stress test of fill, 64-bit
+panel pointers and HBM sizing on one 180 GB B200.  Sparsity factor 1e-5 (nnz(A) = 9.0e7 after the no-relatives
+filter): SURVEY 8d allows sf <= 3.3e-5; at 2e-5 the panels alone take 141 GB and at 3.3e-5 221 GB (symbolic sizing on
+the host, profiles/README.md), so 1e-5 is the densest of the three that factors on one GPU.
+Writes gpurun_out/r2_c5.json.  Usage: python scripts/run_c5.py [n] [sf]"""
+import json, os, sys, time
+import numpy as np, scipy.sparse as sp, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import bench
+from scilmm_b200 import engine as E, pedigree as P
+import scilmm_b200.SparseCholesky
+S = sys.modules["scilmm_b200.SparseCholesky"]
+
+n_sim = int(sys.argv[1]) if len(sys.argv) > 1 else 3000000
+sf = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-5
+out = {"config": "C5", "n_sim": n_sim, "sf": sf}
+t0 = time.time()
+A, H, cov, y, info = bench.make_inputs(n_sim, sf, 2, seed=0, with_household=True)
+n = A.shape[0]
+out.update(info, gen_s=round(time.time() - t0, 1), nnz_household=int(H.nnz))
+E.UPLOAD_THREADS = 8
+free0, total = torch.cuda.mem_get_info()
+
+# ---- HE fit, K = 3
+AoA = P.epistasis(A)
+S.HE_TIMINGS = {}
+t0 = time.perf_counter()
+est = S.HE([A, AoA, H], cov, y.copy())
+torch.cuda.synchronize()
+out["he"] = {"e2e_s": round(time.perf_counter() - t0, 3), "parts_s": {k: round(v, 3) for k, v in S.HE_TIMINGS.items()},
+             "estimates": [float(v) for v in est]}
+S.HE_TIMINGS = None
+ms = E.MatSet([A, AoA, H]); yd = E.to_device(y)
+ms.he_moments_device(yd); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): ms.he_moments_device(yd)
+e1.record(); torch.cuda.synchronize()
+out["he"]["device_ms"] = round(e0.elapsed_time(e1) / 5, 3)
+del ms
+print("HE", out["he"], flush=True)
+
+# ---- one factorization / logdet of V = 0.3 A + 0.15 A o A + 0.55 I
+mats = [A, AoA, sp.eye(n).tocsr()]
+sig = np.array([0.3, 0.15, 0.55])
+ys = y / y.std()
+chol = S.SparseCholesky(rng="device")
+t0 = time.time()
+ses = chol._session(mats, cov, ys)
+torch.cuda.synchronize()
+st = ses.eng.stats()
+out["setup_s"] = round(time.time() - t0, 1)
+out["setup_parts_s"] = {k: round(v, 2) for k, v in ses.timings.items()}
+out["symbolic"] = {k: st[k] for k in ("n", "nsuper", "nlevels", "nnzL", "lsize", "max_front_rows", "max_super_cols",
+                                      "ncomponents", "launches", "device_bytes", "flops", "t_order", "t_symbolic")}
+out["panel_pointers_exceed_int32"] = bool(st["lsize"] > 2 ** 31)
+print("session", out["setup_s"], out["symbolic"], flush=True)
+def factor():
+    ses.factor_at(sig)
+    return ses.eng.logdet()
+t0 = time.perf_counter(); ld1 = factor(); torch.cuda.synchronize(); t_first = time.perf_counter() - t0
+t0 = time.perf_counter(); ld2 = factor(); torch.cuda.synchronize(); t_fac = time.perf_counter() - t0
+free1, _ = torch.cuda.mem_get_info()
+out["factor"] = {"first_s": round(t_first, 3), "seconds": round(t_fac, 3), "tflops": round(st["flops"] / t_fac / 1e12, 2),
+                 "logdet": ld1, "logdet_bitwise_repeatable": bool(ld1 == ld2),
+                 "hbm_in_use_gb": round((total - free1) / 1e9, 1), "hbm_total_gb": round(total / 1e9, 1)}
+B = torch.randn(n, 2, dtype=torch.float64, device="cuda")
+X = ses.eng.solve_(B.clone())
+VX = sum(float(sig[k]) * ses.matset.spmm(k, X) for k in range(3))
+out["factor"]["solve_residual_rel"] = float((VX - B).abs().max() / B.abs().max())
+t0 = time.perf_counter(); ses.eng.solve_(B.clone()); torch.cuda.synchronize()
+out["factor"]["solve_2rhs_s"] = round(time.perf_counter() - t0, 3)
+print(json.dumps(out), flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r2_c5.json"), "w"), indent=1)
+assert out["factor"]["logdet_bitwise_repeatable"] and out["factor"]["solve_residual_rel"] < 1e-10
