@@ -378,8 +378,11 @@ struct PhaseBuilder {
            (op.a_sk % 2) == 0 && (op.b_sk % 2) == 0 && op.a_sk > 0 && op.b_sk > 0 && op.K >= 64;
   }
   void push(const GemmOp& op, bool small_tiles) {
+    // an in-place op (C == A: the triangular panel multiply) must stay inside ONE tile column; the TMA tile grid is
+    // shifted by one column when B starts on an odd element, which would split N = 128 over two tile columns
+    const bool tma_splits_inplace = op.C == op.A && op.N + (int)(((uintptr_t)op.B >> 3) & 1) > 128;
     if (small_tiles) small.push_back(op);
-    else if (tma_ok(op)) tma.push_back(op);
+    else if (tma_ok(op) && !tma_splits_inplace) tma.push_back(op);
     else big.push_back(op);
   }
   // split op along K into S parts whose partial products land in the workspace, + the fixed-order reduction
@@ -1402,7 +1405,7 @@ int slmm_chol_analyze(int32_t n, const int32_t* indptr, const int32_t* indices, 
       const int nbo = (int)std::min<int64_t>(ns, (int64_t)(ob + 1) * NBO) - ob * NBO;
       if (nbo > NBI) {
         if (ns <= NBO) h->wblocks.push_back({h->wptr[s] + w, nbo, 0});   // wide fronts build W during the factorization
-        w += (int64_t)nbo * nbo;
+        w += ((int64_t)nbo * nbo + 1) & ~(int64_t)1;      // every slot starts on a 16-byte boundary (TMA operands)
       }
     }
     h->wptr[s + 1] = h->wptr[s] + w;

@@ -17,6 +17,11 @@
 // index): results are bit-reproducible.  The tiling is built once per session on the device (two radix sorts).
 #include <algorithm>
 #include <cassert>
+#ifdef SLMM_DEBUG_ASSERTS
+#define QT_ASSERT(x) assert(x)
+#else
+#define QT_ASSERT(x) ((void)0)   // device-side checks of the tile structures: build with -DSLMM_DEBUG_ASSERTS
+#endif
 #include <cstring>
 #include <vector>
 
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(256) qt_keys2_kernel(const uint64_t* __restric
     const int rb = (int)(key >> 34), pj = (int)((key >> 6) & 0xfffffffull), lrow = (int)(key & 63);
     const int g = gidx[e] - 1;                       // global index of the (row block, column) pair
     const int dcol = g - dcol_base[rb];
-    assert(dcol >= 0);
+    QT_ASSERT(dcol >= 0);
     const int tile = tile_base[rb] + dcol / QT_CH, lcol = dcol % QT_CH;
     const int diag = (rb * QT_RB + lrow) == pj ? 1 : 0;
     keys2[e] = ((uint64_t)tile << 13) | ((uint64_t)lrow << 7) | ((uint64_t)lcol << 1) | (uint64_t)diag;
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(256) qt_values_kernel(const uint16_t* __restri
                                                         const double* __restrict__ data, int64_t m, int64_t nnz,
                                                         double* __restrict__ out) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x) {
-    assert((int64_t)pos[e] < nnz);
+    QT_ASSERT((int64_t)pos[e] < nnz);
     out[e] = ((rc[e] & 1) ? 1.0 : 2.0) * data[pos[e]];          // off-diagonal entries stand for both triangles
   }
 }
@@ -167,16 +172,16 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   for (int q = tid; q < QT_CH * LDX + QT_RB * G * QT_NB; q += 256) qsm[q] = 0.0;   // incl. the padding columns of Xs
   int pair = a.pair_base[blockIdx.x];
   __syncthreads();
-  assert(t_begin >= 0 && t_begin <= t_end && t_end <= a.ntiles);
+  QT_ASSERT(t_begin >= 0 && t_begin <= t_end && t_end <= a.ntiles);
   for (int t = t_begin; t < t_end; t++) {
     const int rb = a.tile_rb[t], nc = a.tile_nc[t], dc0 = a.tile_dc0[t];
     const int64_t tb = a.tile_ptr[t];
-    assert(rb >= 0 && rb < a.nrb && nc > 0 && nc <= QT_CH && dc0 >= 0 && (int64_t)dc0 + nc <= a.ndistinct);
-    assert(tb >= 0 && a.tile_ptr[t + 1] >= tb && a.tile_ptr[t + 1] <= a.nentries);
+    QT_ASSERT(rb >= 0 && rb < a.nrb && nc > 0 && nc <= QT_CH && dc0 >= 0 && (int64_t)dc0 + nc <= a.ndistinct);
+    QT_ASSERT(tb >= 0 && a.tile_ptr[t + 1] >= tb && a.tile_ptr[t + 1] <= a.nentries);
     // stage the tile: row starts + the nc gathered rows of X
     if (tid <= QT_RB) rp_s[tid] = a.rowptr[(int64_t)t * (QT_RB + 1) + tid];
     for (int c = warp; c < nc; c += 8) {
-      assert(a.dcols[dc0 + c] >= 0 && a.dcols[dc0 + c] < a.n);
+      QT_ASSERT(a.dcols[dc0 + c] >= 0 && a.dcols[dc0 + c] < a.n);
       const double* src = X + (int64_t)a.dcols[dc0 + c] * ncx;
       double* dst = Xs + c * LDX;
       for (int j = lane; j < ncx; j += 32) qt_cp_async8(dst + j, src + j);
@@ -185,13 +190,20 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     __syncthreads();
     for (int lr = warp; lr < QT_RB; lr += 8) {
       const int e0 = rp_s[lr], e1 = rp_s[lr + 1];
-      assert(e0 <= e1 && tb + e1 <= a.tile_ptr[t + 1]);
+      QT_ASSERT(e0 <= e1 && tb + e1 <= a.tile_ptr[t + 1]);
       if (e0 == e1) continue;
       double acc[G][CPL];
 #pragma unroll
       for (int g = 0; g < G; g++)
 #pragma unroll
         for (int c = 0; c < CPL; c++) acc[g][c] = 0.0;
+      // the row's own x_i: issued before the entry loop so its latency hides behind it
+      const int row = a.rowid[rb * QT_RB + lr];
+      QT_ASSERT(row >= 0 && row < a.n);
+      const double* xi = X + (int64_t)row * ncx + lane;
+      double xrow[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; c++) xrow[c] = (lane + 32 * c < ncx) ? xi[32 * c] : 0.0;
       for (int p0 = e0; p0 < e1; p0 += 32) {
         const int pl = p0 + lane;
         const int myrc = pl < e1 ? (int)a.rc[tb + pl] : 0;
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
         const int cnt = min(32, e1 - p0);
         for (int k = 0; k < cnt; k++) {
           const int lcol = __shfl_sync(0xffffffffu, myrc, k) >> 1;
-          assert(lcol >= 0 && lcol < nc);
+          QT_ASSERT(lcol >= 0 && lcol < nc);
           double v[G];
 #pragma unroll
           for (int g = 0; g < G; g++) v[g] = __shfl_sync(0xffffffffu, myv[g], k);
@@ -214,15 +226,10 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
           }
         }
       }
-      const int row = a.rowid[rb * QT_RB + lr];
-      assert(row >= 0 && row < a.n);
-      const double* xi = X + (int64_t)row * ncx + lane;
 #pragma unroll
-      for (int c = 0; c < CPL; c++) {
-        const double x = (lane + 32 * c < ncx) ? xi[32 * c] : 0.0;
+      for (int c = 0; c < CPL; c++)
 #pragma unroll
-        for (int g = 0; g < G; g++) dot[g][c] += acc[g][c] * x;
-      }
+        for (int g = 0; g < G; g++) dot[g][c] += acc[g][c] * xrow[c];
       if (lane < nb) {                               // this warp owns the row: plain accumulation
 #pragma unroll
         for (int g = 0; g < G; g++) hbS[(lr * G + g) * QT_NB + lane] += acc[g][0];

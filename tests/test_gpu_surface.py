@@ -602,3 +602,65 @@ def test_tiled_quadforms_and_gram(case, request, slmm, eng):
         ses.use_tiles = tiles
         out.append(ses.evaluate(sig, True, 40, Z=Z))
     assert out[0][0] == out[1][0] and rel_err(out[0][1], out[1][1]) < 1e-11
+
+
+def test_wide_front_after_odd_sized_inverse_block(slmm, eng):
+    """A wide front (> 1024 columns: blocked panel chain, in-place triangular panel multiply through W) that FOLLOWS
+    a supernode whose block inverse has an odd number of entries.  The TMA tile grid is shifted by one column for an
+    operand on an odd element; an in-place multiply split over two tile columns reads what the other column
+    overwrites (seen as a 4e-3 solve residual at the 250K bench size, never below 100K individuals: no wide fronts
+    there).  Against LAPACK, on both orderings, for the logdet, a solve and L*Z."""
+    rng = np.random.default_rng(21)
+    n1, n2 = 333, 2601
+    def spd(m):
+        B = rng.standard_normal((m, m))
+        return B @ B.T / m + 2.0 * np.eye(m)
+    V = np.zeros((n1 + n2, n1 + n2))
+    V[:n1, :n1] = spd(n1)
+    V[n1:, n1:] = spd(n2)
+    Vs = sp.csc_matrix(V)
+    sign, ld = np.linalg.slogdet(V)
+    Bm = rng.standard_normal((n1 + n2, 7))
+    want = np.linalg.solve(V, Bm)
+    for ordering in ("natural", "nesdis"):
+        f = slmm.SparseCholesky(ordering_method=ordering)(Vs)
+        assert abs(f.logdet() - ld) < 1e-9 * abs(ld), ordering
+        assert rel_err(f(Bm), want) < 1e-10, ordering
+        P = f.P()
+        Lref = la.cholesky(V[P][:, P], lower=True)
+        Z = rng.standard_normal((n1 + n2, 130))
+        got = f.lmul(eng.to_device(Z)).cpu().numpy()
+        assert rel_err(got, (Lref @ Z)[np.argsort(P)]) < 1e-11, ordering
+
+
+def test_headline_size_250k_properties(slmm, eng):
+    """BASELINE config 1 as simulated for the headline metric (250,000 individuals, K = 3, 10 covariates, wide
+    fronts of several thousand columns): size-independent properties of the factor at FULL size - V x = b for every
+    RHS-width class of the solve schedules (narrow streaming kernels, DMMA tiles), L*Z undone by the forward sweep,
+    bitwise repeatability of logdet and (LZ)' V^-1 (LZ) = Z'Z.  (scripts/solve_check.py runs the same residuals
+    with SLMM_TMA=0 / SLMM_SKINNY=0 twins.)"""
+    import torch, bench
+    from scilmm_b200 import pedigree as P
+    A, _, cov, y, info = bench.make_inputs(250000, 1e-3, 10)
+    n = A.shape[0]
+    mats = [A, P.epistasis(A), sp.eye(n).tocsr()]
+    sig = np.array([0.3, 0.15, 0.55])
+    chol = slmm.SparseCholesky(rng="device")
+    ses = chol._session(mats, cov, y / y.std())
+    ses.factor_at(sig)
+    ld1 = ses.eng.logdet()
+    ses.factor_at(sig)
+    assert ses.eng.logdet() == ld1
+    assert ses.eng.stats()["max_super_cols"] > 1024          # the blocked wide-front path is exercised
+    torch.manual_seed(0)
+    for k in (1, 2, 4, 8, 12, 16, 32, 128):
+        B = torch.randn(n, k, dtype=torch.float64, device="cuda")
+        X = ses.eng.solve_(B.clone())
+        VX = sum(float(sig[j]) * ses.matset.spmm(j, X) for j in range(3))
+        assert float((VX - B).abs().max() / B.abs().max()) < 1e-11, k
+        LZ = ses.eng.lmul(B.clone())
+        Y = ses.eng.solve_(LZ.clone(), mode=1)                 # L^-1 (L Z): Z with its rows permuted
+        assert float(((Y * Y).sum(0) - (B * B).sum(0)).abs().max() / (B * B).sum(0).max()) < 1e-12, k
+        # (L Z)' V^-1 (L Z) = Z'Z column by column (lmul returns P'LZ; V^-1 = P' L^-T L^-1 P)
+        q1, q2 = (LZ * ses.eng.solve_(LZ.clone())).sum(0), (B * B).sum(0)
+        assert float(((q1 - q2).abs() / q2).max()) < 1e-11, k
