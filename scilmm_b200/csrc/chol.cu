@@ -447,7 +447,12 @@ struct PhaseBuilder {
     // what this one overwrites)
     const bool force_big = op.flags & GF_BIGTILE;
     op.flags &= ~GF_BIGTILE;
-    const bool small_tiles = !force_big && (!(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128));
+    // lower-masked updates inside a wide front's diagonal block (K = 64 in-block steps, the K = 1024 update of the next
+    // block's 1024 x 1024 diagonal part): at most 36 useful 128 x 128 tiles sit on the critical chain with one long K
+    // loop each; 64 x 64 tiles put 4x the CTAs on it (0.152 -> ~0.05 ms for the K = 1024 step, 25 -> ~13 us for K = 64)
+    static const bool chain_small = !(getenv("SLMM_CHAIN_SMALL") && getenv("SLMM_CHAIN_SMALL")[0] == '0');
+    const bool small_tiles = !force_big && (!(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128) ||
+                                            (chain_small && lower && tb <= 64));
     const int64_t tiles = small_tiles ? ts : tb;
     if (allow_split && !lower && !(op.flags & GF_TRIL_B) && tiles <= 148 && op.K >= 256 && op.C != op.A) {
       int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 64), std::max<int64_t>(1, 148 / tiles));   // one wave of CTAs
