@@ -63,6 +63,11 @@ int slmm_matset_set_symmetric(slmm_matset_t* ms, int32_t k, int32_t flag);
 /* Pageable host array -> device through a ring of persistent pinned buffers filled by `threads` worker threads
  * (0 = default 4); ordered with the default stream on both sides.  The e2e upload of the scipy CSR arrays. */
 int slmm_upload_h2d(void* d_dst, const void* h_src, int64_t nbytes, int32_t threads);
+/* Pitched host block -> pitched device block (`rows` pieces of `width_bytes`): the local probe columns of a host
+ * n x s block Z (the reference's np.random.randn(n, sim_num), SparseCholesky.py:98) go up without packing the slice
+ * on the host.  Pinned or pageable source; returns when the copy is done. */
+int slmm_upload_h2d_2d(void* d_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t width_bytes,
+                       int64_t rows);
 int slmm_matset_nnz(const slmm_matset_t* ms, int32_t k, int64_t* out);
 int slmm_matset_values(const slmm_matset_t* ms, int32_t k, const double** d_data_out);
 

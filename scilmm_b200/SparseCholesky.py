@@ -315,17 +315,18 @@ class RemlSession(object):
             else:
                 Z = self.eng.probe_normals(self.n, col_end - col_begin, col_begin, self.functor.seed, self.n_eval)
                 col_begin, col_end = 0, Z.shape[1]
+        sliced = bool(col_begin or col_end != Z.shape[1])
         if not torch.is_tensor(Z):
-            Z = np.asarray(Z, dtype=np.float64)
-            if col_begin or col_end != Z.shape[1]:        # slice on the host: only the local columns are uploaded
-                Z = np.ascontiguousarray(Z[:, col_begin:col_end])
-            Z = _eng.to_device(Z, torch)
+            Z = np.ascontiguousarray(Z, dtype=np.float64)
+            # only the local columns are uploaded, by one pitched DMA (no packing of the slice on the host)
+            Z = _eng.upload_columns(Z, col_begin, col_end, torch) if sliced else _eng.to_device(Z, torch)
+        elif not Z.is_cuda:
+            if sliced and Z.is_contiguous() and Z.dtype == torch.float64:
+                Z = _eng.upload_columns(Z, col_begin, col_end, torch)
+            else:
+                Z = (Z[:, col_begin:col_end] if sliced else Z).contiguous().to("cuda", non_blocking=True)
         else:
-            if col_begin or col_end != Z.shape[1]:
-                Z = Z[:, col_begin:col_end]
-            if not Z.is_cuda:
-                Z = Z.contiguous().to("cuda", non_blocking=True)
-            Z = Z.contiguous()
+            Z = (Z[:, col_begin:col_end] if sliced else Z).contiguous()
         U = self.eng.lmul(Z)
         return self.eng.solve_(U)
 

@@ -44,6 +44,7 @@ SIGNATURES = {
     "slmm_matset_symmetry_hash": (C.c_int, [vp, i32, vp]),
     "slmm_matset_set_symmetric": (C.c_int, [vp, i32, i32]),
     "slmm_upload_h2d": (C.c_int, [vp, vp, i64, i32]),
+    "slmm_upload_h2d_2d": (C.c_int, [vp, i64, vp, i64, i64, i64]),
     "slmm_matset_nnz": (C.c_int, [vp, i32, C.POINTER(i64)]),
     "slmm_matset_values": (C.c_int, [vp, i32, pp]),
     "slmm_he_moments": (C.c_int, [vp, vp, i32, i32, vp]),

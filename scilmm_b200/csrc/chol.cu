@@ -415,11 +415,12 @@ struct PhaseBuilder {
     if (!f1 && op.b_sk != 1) return false;
     if (!f1 && (op.flags & GF_TRIL_B)) return false;
     std::vector<GemmOp>& dst = f1 ? sk1 : sk2;
-    const int cols = f1 ? SK_F1_COLS : SK_F2_COLS, kmin = f1 ? 128 : 64;
+    const int cols = f1 ? SK_F1_COLS : SK_F2_COLS, kmin = 64;
     const int64_t nj = (op.N + cols - 1) / cols;
-    // enough CTAs to keep the HBM pipe full (streaming kernels: ~4 resident CTAs per SM), K parts of >= kmin
+    // enough CTAs to keep the HBM pipe full, K parts of >= kmin.  F1 is bound by (k rounds per thread) x (memory
+    // latency): 8 resident 128-thread CTAs per SM with 16 loads in flight each cover the bandwidth-latency product
     int S = 1;
-    const int64_t target = 148 * 4;
+    const int64_t target = f1 ? 148 * 8 : 148 * 4;
     const bool can_split = allow_split && op.C != op.A;
     if (can_split && nj < target) S = (int)std::min<int64_t>((target + nj - 1) / nj, std::max(1, op.K / kmin));
     if (!f1) S = std::max(S, (op.K + SK_F2_KMAX - 1) / SK_F2_KMAX);      // F2 stages its whole K range of A

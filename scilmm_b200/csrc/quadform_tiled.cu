@@ -36,6 +36,7 @@ namespace slmm {
 constexpr int QT_RB = 64;     // permuted rows per row block
 constexpr int QT_CH = 64;     // distinct columns per tile (rows of the dense block staged in shared memory)
 constexpr int QT_NB = 16;     // widest narrow block
+constexpr int QT_ECAP = 768;  // entries of a tile staged in shared memory (larger tiles read them from global memory)
 
 // ---- build ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qt_keys_kernel(const int32_t* __restrict__ ap, const int32_t* __restrict__ ai, int n,
@@ -161,6 +162,8 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   extern __shared__ double qsm[];
   double* Xs = qsm;                                   // [QT_CH][LDX]  gathered rows of the dense block
   double* hbS = Xs + QT_CH * LDX;                     // [QT_RB][G][QT_NB]  narrow-block row products of this row block
+  double* vS = hbS + QT_RB * G * QT_NB;               // [G][QT_ECAP]  values of the tile's entries
+  uint16_t* rcS = reinterpret_cast<uint16_t*>(vS + G * QT_ECAP);      // [QT_ECAP]  local column << 1 | diagonal flag
   __shared__ uint16_t rp_s[QT_RB + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_begin = a.cta_begin[blockIdx.x], t_end = a.cta_begin[blockIdx.x + 1];
@@ -180,6 +183,17 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     QT_ASSERT(tb >= 0 && a.tile_ptr[t + 1] >= tb && a.tile_ptr[t + 1] <= a.nentries);
     // stage the tile: row starts + the nc gathered rows of X
     if (tid <= QT_RB) rp_s[tid] = a.rowptr[(int64_t)t * (QT_RB + 1) + tid];
+    // the tile's entries: a warp that fetched them row by row exposed one global round trip per row (8 rows per warp
+    // and tile, ~0.7 us each, with only 16 warps per SM to hide it)
+    const int ne = (int)(a.tile_ptr[t + 1] - tb);
+    const bool staged = ne <= QT_ECAP;
+    if (staged) {
+      for (int e = tid; e < ne; e += 256) {
+#pragma unroll
+        for (int g = 0; g < G; g++) qt_cp_async8(vS + g * QT_ECAP + e, a.vals[g] + tb + e);
+      }
+      for (int e = tid; e < ne; e += 256) rcS[e] = a.rc[tb + e];
+    }
     for (int c = warp; c < nc; c += 8) {
       QT_ASSERT(a.dcols[dc0 + c] >= 0 && a.dcols[dc0 + c] < a.n);
       const double* src = X + (int64_t)a.dcols[dc0 + c] * ncx;
@@ -206,10 +220,10 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
       for (int c = 0; c < CPL; c++) xrow[c] = (lane + 32 * c < ncx) ? xi[32 * c] : 0.0;
       for (int p0 = e0; p0 < e1; p0 += 32) {
         const int pl = p0 + lane;
-        const int myrc = pl < e1 ? (int)a.rc[tb + pl] : 0;
+        const int myrc = pl < e1 ? (int)(staged ? rcS[pl] : a.rc[tb + pl]) : 0;
         double myv[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) myv[g] = pl < e1 ? __ldcs(a.vals[g] + tb + pl) : 0.0;
+        for (int g = 0; g < G; g++) myv[g] = pl < e1 ? (staged ? vS[g * QT_ECAP + pl] : __ldcs(a.vals[g] + tb + pl)) : 0.0;
         const int cnt = min(32, e1 - p0);
         for (int k = 0; k < cnt; k++) {
           const int lcol = __shfl_sync(0xffffffffu, myrc, k) >> 1;
@@ -325,7 +339,7 @@ __global__ void qt_reduce_kernel(const double* __restrict__ partial, int nblocks
 template <int CPL, int G>
 static void qt_launch(const QuadTiles& T, const QtArgs& a, const double* d_X, int ncx, int nb, double* part_dots,
                       double* part_gram, double* d_dots, double* d_gram) {
-  const size_t smem = ((size_t)QT_CH * CPL * 32 + (size_t)QT_RB * G * QT_NB) * sizeof(double);
+  const size_t smem = ((size_t)QT_CH * CPL * 32 + (size_t)QT_RB * G * QT_NB + (size_t)G * QT_ECAP) * sizeof(double) + QT_ECAP * sizeof(uint16_t);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_OK(cudaFuncSetAttribute(quadform_tiled_kernel<CPL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

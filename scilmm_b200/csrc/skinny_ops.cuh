@@ -71,12 +71,21 @@ __global__ void __launch_bounds__(SK_F1_COLS) skinny_f1_kernel(const GemmOp* __r
     if (!active) continue;
     const int kl = min(kc, kmine - k0);
     int k = 0;
-    for (; k + 8 <= kl; k += 8) {                      // 8 independent loads in flight per thread
-      double b[8];
+    for (; k + 16 <= kl; k += 16) {                    // 16 independent loads in flight per thread: the kernel is bound
+      double b[16];                                    // by rounds x memory latency, not by issue
 #pragma unroll
-      for (int u = 0; u < 8; u++) b[u] = __ldcs(Bj + (int64_t)(k0 + k + u) * b_sk);
+      for (int u = 0; u < 16; u++) b[u] = __ldcs(Bj + (int64_t)(k0 + k + u) * b_sk);
 #pragma unroll
-      for (int u = 0; u < 8; u++)
+      for (int u = 0; u < 16; u++)
+#pragma unroll
+        for (int i = 0; i < MT; i++) acc[i] += As[(k + u) * MT + i] * b[u];
+    }
+    for (; k + 4 <= kl; k += 4) {
+      double b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) b[u] = __ldcs(Bj + (int64_t)(k0 + k + u) * b_sk);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int i = 0; i < MT; i++) acc[i] += As[(k + u) * MT + i] * b[u];
     }

@@ -1414,6 +1414,20 @@ int slmm_upload_h2d(void* d_dst, const void* h_src, int64_t nbytes, int32_t thre
   SLMM_CATCH
 }
 
+int slmm_upload_h2d_2d(void* d_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t width_bytes,
+                       int64_t rows) {
+  SLMM_TRY
+  if (!d_dst || !h_src || width_bytes < 0 || rows < 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+    throw std::invalid_argument("bad arguments");
+  if (width_bytes == 0 || rows == 0) return SLMM_OK;
+  // the DMA engine walks the pitched source: no host-side packing of the column slice
+  CUDA_OK(cudaMemcpy2DAsync(d_dst, (size_t)dst_pitch, h_src, (size_t)src_pitch, (size_t)width_bytes, (size_t)rows,
+                            cudaMemcpyHostToDevice, 0));
+  CUDA_OK(cudaStreamSynchronize(0));            // the host block may be reused by the caller right away
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
 int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out) {
   if (!ms || k < 0 || k >= ms->K || !out) return SLMM_ERR_INVALID;
   *out = ms->m[k].pattern;

@@ -65,6 +65,26 @@ def to_device(a, torch=None):
     return out
 
 
+def upload_columns(Z, col_begin, col_end, torch=None):
+    """Columns [col_begin, col_end) of a C-ordered host float64 block (ndarray or CPU tensor, pinned or not) as a
+    contiguous CUDA tensor: one pitched DMA, no host-side packing of the slice (slmm_upload_h2d_2d)."""
+    torch = torch or require_cuda()
+    n, s = int(Z.shape[0]), int(Z.shape[1])
+    if torch.is_tensor(Z):
+        if Z.dtype != torch.float64 or not Z.is_contiguous() or Z.is_cuda:
+            raise ValueError("upload_columns needs a contiguous float64 host block")
+        src, itemsize = Z.data_ptr(), 8
+    else:
+        if Z.dtype != np.float64 or not Z.flags.c_contiguous:
+            raise ValueError("upload_columns needs a C-ordered float64 host block")
+        src, itemsize = Z.ctypes.data, 8
+    w = int(col_end) - int(col_begin)
+    out = torch.empty(n, w, dtype=torch.float64, device="cuda")
+    check(lib().slmm_upload_h2d_2d(out.data_ptr(), w * itemsize, src + int(col_begin) * itemsize, s * itemsize,
+                                   w * itemsize, n))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ symbolic
 class SymbolicView(object):
     """Host-only symbolic analysis (no GPU needed)."""

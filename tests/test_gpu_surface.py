@@ -664,3 +664,20 @@ def test_headline_size_250k_properties(slmm, eng):
         # (L Z)' V^-1 (L Z) = Z'Z column by column (lmul returns P'LZ; V^-1 = P' L^-T L^-1 P)
         q1, q2 = (LZ * ses.eng.solve_(LZ.clone())).sum(0), (B * B).sum(0)
         assert float(((q1 - q2).abs() / q2).max()) < 1e-11, k
+
+
+def test_upload_columns_pitched_copy(eng):
+    """slmm_upload_h2d_2d: a column slice of a host block (ndarray, pageable and pinned CPU tensors) arrives as a
+    contiguous device block, bit for bit; degenerate and full-width slices; bad layouts are refused."""
+    import torch
+    rng = np.random.default_rng(3)
+    Z = rng.standard_normal((5003, 37))
+    for lo, hi in ((0, 37), (5, 19), (36, 37), (0, 1), (7, 7)):
+        for src in (Z, torch.from_numpy(Z), torch.from_numpy(Z).pin_memory()):
+            got = eng.upload_columns(src, lo, hi)
+            assert got.is_cuda and got.is_contiguous() and tuple(got.shape) == (5003, hi - lo)
+            assert np.array_equal(got.cpu().numpy(), Z[:, lo:hi])
+    with pytest.raises(ValueError):
+        eng.upload_columns(np.asfortranarray(Z), 0, 3)
+    with pytest.raises(ValueError):
+        eng.upload_columns(Z.astype(np.float32), 0, 3)
