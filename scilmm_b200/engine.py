@@ -80,6 +80,8 @@ def upload_columns(Z, col_begin, col_end, torch=None):
         src, itemsize = Z.ctypes.data, 8
     w = int(col_end) - int(col_begin)
     out = torch.empty(n, w, dtype=torch.float64, device="cuda")
+    if n == 0 or w <= 0:
+        return out
     check(lib().slmm_upload_h2d_2d(out.data_ptr(), w * itemsize, src + int(col_begin) * itemsize, s * itemsize,
                                    w * itemsize, n))
     return out
