@@ -202,9 +202,33 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
+    // first entry chunk of the warp's next row, fetched one row ahead (tiles too large for the staging buffer)
+    int nx_rc = 0;
+    double nx_v[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) nx_v[g] = 0.0;
+    if (!staged) {
+      const int pl = rp_s[warp] + lane;
+      if (pl < rp_s[warp + 1]) {
+        nx_rc = (int)a.rc[tb + pl];
+#pragma unroll
+        for (int g = 0; g < G; g++) nx_v[g] = __ldcs(a.vals[g] + tb + pl);
+      }
+    }
     for (int lr = warp; lr < QT_RB; lr += 8) {
       const int e0 = rp_s[lr], e1 = rp_s[lr + 1];
       QT_ASSERT(e0 <= e1 && tb + e1 <= a.tile_ptr[t + 1]);
+      const int cur_rc = nx_rc;
+      double cur_v[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) cur_v[g] = nx_v[g];
+      if (!staged && lr + 8 < QT_RB) {
+        const int pl = rp_s[lr + 8] + lane;
+        const bool in = pl < rp_s[lr + 9];
+        nx_rc = in ? (int)a.rc[tb + pl] : 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) nx_v[g] = in ? __ldcs(a.vals[g] + tb + pl) : 0.0;
+      }
       if (e0 == e1) continue;
       double acc[G][CPL];
 #pragma unroll
@@ -220,10 +244,12 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
       for (int c = 0; c < CPL; c++) xrow[c] = (lane + 32 * c < ncx) ? xi[32 * c] : 0.0;
       for (int p0 = e0; p0 < e1; p0 += 32) {
         const int pl = p0 + lane;
-        const int myrc = pl < e1 ? (int)(staged ? rcS[pl] : a.rc[tb + pl]) : 0;
+        const bool first = p0 == e0 && !staged;                 // already in registers
+        const int myrc = pl < e1 ? (first ? cur_rc : (int)(staged ? rcS[pl] : a.rc[tb + pl])) : 0;
         double myv[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) myv[g] = pl < e1 ? (staged ? vS[g * QT_ECAP + pl] : __ldcs(a.vals[g] + tb + pl)) : 0.0;
+        for (int g = 0; g < G; g++)
+          myv[g] = pl < e1 ? (first ? cur_v[g] : (staged ? vS[g * QT_ECAP + pl] : __ldcs(a.vals[g] + tb + pl))) : 0.0;
         const int cnt = min(32, e1 - p0);
         for (int k = 0; k < cnt; k++) {
           const int lcol = __shfl_sync(0xffffffffu, myrc, k) >> 1;
@@ -463,18 +489,30 @@ int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm,
     std::vector<int32_t> perm = qt_to_host(d_perm, (size_t)n), rowid((size_t)nrb * QT_RB, -1);
     for (int i = 0; i < n; i++) rowid[i] = perm[i];
     T.rowid = dev_upload(rowid.data(), rowid.size());
-    // static partition of the tiles over the CTAs (two resident per SM), balanced by entries + a per-tile constant
+    // static partition of the tiles over the CTAs (two resident per SM) by a cost model in units of one entry:
+    // entries + 20 per non-empty row (a warp exposes the latency of the row's own x_i and of the first entry chunk)
+    // + 400 per tile (metadata, column list, gather: three dependent round trips).  Entries alone left one CTA with
+    // 25 646 row segments against a mean of 4 632 (the pass took as long as that CTA: 5 of the 6 ms).
     std::vector<int64_t> tptr = qt_to_host(T.tile_ptr, (size_t)ntiles + 1);
+    std::vector<uint16_t> rptr = qt_to_host(T.rowptr, (size_t)ntiles * (QT_RB + 1));
     const int ncta = std::max(1, std::min(148 * 2, ntiles));
     std::vector<int32_t> cta_begin(ncta + 1, ntiles);
     {
-      const double per_tile = 160.0;
-      const double total = (double)m + per_tile * ntiles;
+      const double per_tile = 400.0, per_row = 20.0;
+      std::vector<double> cost((size_t)ntiles);
+      double total = 0;
+      for (int t = 0; t < ntiles; t++) {
+        int rows = 0;
+        const uint16_t* rp = rptr.data() + (size_t)t * (QT_RB + 1);
+        for (int r = 0; r < QT_RB; r++) rows += rp[r + 1] > rp[r];
+        cost[t] = (double)(tptr[t + 1] - tptr[t]) + per_row * rows + per_tile;
+        total += cost[t];
+      }
       double acc = 0;
       int cta = 0;
       cta_begin[0] = 0;
       for (int t = 0; t < ntiles; t++) {
-        acc += (double)(tptr[t + 1] - tptr[t]) + per_tile;
+        acc += cost[t];
         while (cta + 1 < ncta && acc >= total * (cta + 1) / ncta) cta_begin[++cta] = t + 1;
       }
       for (int q = cta + 1; q <= ncta; q++) cta_begin[q] = ntiles;
