@@ -129,6 +129,9 @@ int slmm_matset_pattern_id(const slmm_matset_t* ms, int32_t k, int32_t* out);
 int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm, const int32_t* d_iperm);
 /* out4: tiles, entries on/below the diagonal, distinct (row block, column) pairs, CTAs of the pass */
 int slmm_matset_tile_stats(const slmm_matset_t* ms, int32_t k, int64_t* out4);
+/* Developer profile of the last tiled pass: out[c*4 + 0..3] = tiles, non-empty rows, entries of CTA c's tile range and
+ * the clock64 span the CTA took (what the partition's cost model is fitted to). */
+int slmm_matset_tile_cta_profile(const slmm_matset_t* ms, int32_t k, int64_t* out, int32_t ncta);
 int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols, int32_t nb,
                         double* d_dots, double* d_gram_half);
 /* *out = 1 when the n x n CSR matrix in device memory equals its transpose bit for bit (pattern and values).

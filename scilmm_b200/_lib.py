@@ -38,6 +38,7 @@ SIGNATURES = {
     "slmm_matset_bind_device": (C.c_int, [vp, i32, vp, vp, vp, i64, i32]),
     "slmm_matset_build_tiles": (C.c_int, [vp, i32, vp, vp]),
     "slmm_matset_tile_stats": (C.c_int, [vp, i32, vp]),
+    "slmm_matset_tile_cta_profile": (C.c_int, [vp, i32, vp, i32]),
     "slmm_quadform_tiled": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp]),
     "slmm_chol_device_perm": (C.c_int, [vp, pp, pp]),
     "slmm_matset_set_row_range": (C.c_int, [vp, i32, i32]),

@@ -48,11 +48,13 @@ struct QuadTiles {
   int32_t* pair_rb = nullptr;       // [npairs] row block of every pair
   double* hpairs = nullptr;         // [npairs][64][2][16] narrow-block row products, one block per pair
   int npairs = 0;
+  std::vector<int64_t> cta_stats;    // [ncta][3] tiles, non-empty rows, entries of every CTA's range (host copy)
+  long long* cta_cycles = nullptr;   // [ncta] clock64 span of every CTA in the last pass (developer profile)
   std::vector<double*> vals;        // per matrix of the set sharing this pattern: weighted values in tile order
   std::vector<int> vals_of;         // which matrix each vals[] belongs to
   void release() {
     dev_free(tile_ptr); dev_free(tile_rb); dev_free(tile_dc0); dev_free(tile_nc); dev_free(rowptr); dev_free(rc);
-    dev_free(pos); dev_free(dcols); dev_free(rowid); dev_free(cta_begin); dev_free(pair_base); dev_free(pair_rb); dev_free(hpairs);
+    dev_free(pos); dev_free(dcols); dev_free(rowid); dev_free(cta_begin); dev_free(pair_base); dev_free(pair_rb); dev_free(hpairs); dev_free(cta_cycles); cta_cycles = nullptr;
     pair_base = pair_rb = nullptr; hpairs = nullptr; npairs = 0;
     for (double* v : vals) dev_free(v);
     vals.clear(); vals_of.clear();

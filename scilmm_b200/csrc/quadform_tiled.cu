@@ -146,6 +146,7 @@ struct QtArgs {
   const int64_t* tile_ptr;
   const int32_t *tile_rb, *tile_dc0, *tile_nc, *dcols, *rowid, *cta_begin, *pair_base;
   double* hpairs;
+  long long* cta_cycles;
   const uint16_t *rowptr, *rc;
   const double* vals[2];
 };
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   __shared__ uint16_t rp_s[QT_RB + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_begin = a.cta_begin[blockIdx.x], t_end = a.cta_begin[blockIdx.x + 1];
+  const long long clk0 = clock64();
   double dot[G][CPL];
 #pragma unroll
   for (int g = 0; g < G; g++)
@@ -176,32 +178,55 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   int pair = a.pair_base[blockIdx.x];
   __syncthreads();
   QT_ASSERT(t_begin >= 0 && t_begin <= t_end && t_end <= a.ntiles);
+  // metadata of a tile is fetched one tile ahead; all independent loads of the staging phase are issued before any is
+  // consumed (the per-CTA profile put the fixed cost of a tile at 16 000 cycles = 4-5 dependent global round trips)
+  int rb_n = 0, nc_n = 0, dc0_n = 0;
+  int64_t tb_n = 0, te_n = 0;
+  if (t_begin < t_end) {
+    rb_n = a.tile_rb[t_begin]; nc_n = a.tile_nc[t_begin]; dc0_n = a.tile_dc0[t_begin];
+    tb_n = a.tile_ptr[t_begin]; te_n = a.tile_ptr[t_begin + 1];
+  }
   for (int t = t_begin; t < t_end; t++) {
-    const int rb = a.tile_rb[t], nc = a.tile_nc[t], dc0 = a.tile_dc0[t];
-    const int64_t tb = a.tile_ptr[t];
+    const int rb = rb_n, nc = nc_n, dc0 = dc0_n;
+    const int64_t tb = tb_n;
+    const int ne = (int)(te_n - tb_n);
+    if (t + 1 < t_end) {
+      rb_n = a.tile_rb[t + 1]; nc_n = a.tile_nc[t + 1]; dc0_n = a.tile_dc0[t + 1];
+      tb_n = te_n; te_n = a.tile_ptr[t + 2];
+    }
     QT_ASSERT(rb >= 0 && rb < a.nrb && nc > 0 && nc <= QT_CH && dc0 >= 0 && (int64_t)dc0 + nc <= a.ndistinct);
-    QT_ASSERT(tb >= 0 && a.tile_ptr[t + 1] >= tb && a.tile_ptr[t + 1] <= a.nentries);
-    // stage the tile: row starts + the nc gathered rows of X
-    if (tid <= QT_RB) rp_s[tid] = a.rowptr[(int64_t)t * (QT_RB + 1) + tid];
-    // the tile's entries: a warp that fetched them row by row exposed one global round trip per row (8 rows per warp
-    // and tile, ~0.7 us each, with only 16 warps per SM to hide it)
-    const int ne = (int)(a.tile_ptr[t + 1] - tb);
+    QT_ASSERT(tb >= 0 && ne >= 0 && tb + ne <= a.nentries);
+    // stage the tile: row starts, entries (if they fit), the nc gathered rows of X
     const bool staged = ne <= QT_ECAP;
+    const uint16_t v_rp = tid <= QT_RB ? a.rowptr[(int64_t)t * (QT_RB + 1) + tid] : (uint16_t)0;
+    int dcv[QT_CH / 8];
+#pragma unroll
+    for (int q = 0; q < QT_CH / 8; q++) dcv[q] = (warp + 8 * q < nc) ? a.dcols[dc0 + warp + 8 * q] : -1;
+    uint16_t v_rc[QT_ECAP / 256];
+#pragma unroll
+    for (int q = 0; q < QT_ECAP / 256; q++) v_rc[q] = (staged && tid + 256 * q < ne) ? a.rc[tb + tid + 256 * q] : (uint16_t)0;
     if (staged) {
       for (int e = tid; e < ne; e += 256) {
 #pragma unroll
         for (int g = 0; g < G; g++) qt_cp_async8(vS + g * QT_ECAP + e, a.vals[g] + tb + e);
       }
-      for (int e = tid; e < ne; e += 256) rcS[e] = a.rc[tb + e];
     }
-    for (int c = warp; c < nc; c += 8) {
-      QT_ASSERT(a.dcols[dc0 + c] >= 0 && a.dcols[dc0 + c] < a.n);
-      const double* src = X + (int64_t)a.dcols[dc0 + c] * ncx;
-      double* dst = Xs + c * LDX;
+    if (tid <= QT_RB) rp_s[tid] = v_rp;
+#pragma unroll
+    for (int q = 0; q < QT_ECAP / 256; q++)
+      if (staged && tid + 256 * q < ne) rcS[tid + 256 * q] = v_rc[q];
+#pragma unroll
+    for (int q = 0; q < QT_CH / 8; q++) {
+      if (dcv[q] < 0) continue;
+      QT_ASSERT(dcv[q] < a.n);
+      const double* src = X + (int64_t)dcv[q] * ncx;
+      double* dst = Xs + (warp + 8 * q) * LDX;
       for (int j = lane; j < ncx; j += 32) qt_cp_async8(dst + j, src + j);
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
+    // column list of the NEXT tile: its gathered rows of X are pulled into L2 while this tile computes
+    const int dnext = ((a.pad & 1) && t + 1 < t_end && tid < nc_n) ? a.dcols[dc0_n + tid] : -1;
     // first entry chunk of the warp's next row, fetched one row ahead (tiles too large for the staging buffer)
     int nx_rc = 0;
     double nx_v[G];
@@ -275,10 +300,14 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
         for (int g = 0; g < G; g++) hbS[(lr * G + g) * QT_NB + lane] += acc[g][0];
       }
     }
+    if (dnext >= 0) {
+      const char* pf = reinterpret_cast<const char*>(X + (int64_t)dnext * ncx);
+      for (int b = 0; b < ncx * 8; b += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf + b));
+    }
     __syncthreads();
     // end of the row block (or of this CTA's range): park the narrow-block row products of this (CTA, row block)
     // pair in global memory; qt_gram_finish_kernel folds them into the Gram matrix
-    if (nb > 0 && (t + 1 == t_end || a.tile_rb[t + 1] != rb)) {
+    if (nb > 0 && (t + 1 == t_end || rb_n != rb)) {
       double* hp = a.hpairs + (int64_t)pair * (QT_RB * 2 * QT_NB);
       for (int q = tid; q < QT_RB * G * QT_NB; q += 256) { hp[q] = hbS[q]; hbS[q] = 0.0; }
       pair++;
@@ -299,6 +328,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     for (int w = 0; w < 8; w++) s += red[(w * G + g) * LDX + j];
     part_dots[(int64_t)blockIdx.x * G * ncx + q] = s;
   }
+  if (tid == 0) a.cta_cycles[blockIdx.x] = clock64() - clk0;
 }
 
 // Gram fold: Mh[g] += xb_i hb_i' over the rows of every (CTA, row block) pair.  CTA c takes pairs c, c + gridDim, ...
@@ -516,8 +546,20 @@ int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm,
         while (cta + 1 < ncta && acc >= total * (cta + 1) / ncta) cta_begin[++cta] = t + 1;
       }
       for (int q = cta + 1; q <= ncta; q++) cta_begin[q] = ntiles;
+      T.cta_stats.assign((size_t)ncta * 3, 0);
+      for (int c2 = 0; c2 < ncta; c2++)
+        for (int t = cta_begin[c2]; t < cta_begin[c2 + 1]; t++) {
+          const uint16_t* rp = rptr.data() + (size_t)t * (QT_RB + 1);
+          int rows = 0;
+          for (int r = 0; r < QT_RB; r++) rows += rp[r + 1] > rp[r];
+          T.cta_stats[(size_t)c2 * 3] += 1;
+          T.cta_stats[(size_t)c2 * 3 + 1] += rows;
+          T.cta_stats[(size_t)c2 * 3 + 2] += tptr[t + 1] - tptr[t];
+        }
     }
     T.cta_begin = dev_upload(cta_begin.data(), cta_begin.size());
+    T.cta_cycles = dev_alloc<long long>((size_t)ncta);
+    CUDA_OK(cudaMemset(T.cta_cycles, 0, (size_t)ncta * sizeof(long long)));
     // (CTA, row block) pairs: where each CTA parks the narrow-block row products of the row blocks it touches
     std::vector<int32_t> pair_base(ncta + 1, 0), pair_rb;
     for (int c2 = 0; c2 < ncta; c2++) {
@@ -557,6 +599,22 @@ int slmm_matset_tile_stats(const slmm_matset_t* ms, int32_t k, int64_t* out4) {
   return SLMM_OK;
 }
 
+int slmm_matset_tile_cta_profile(const slmm_matset_t* ms, int32_t k, int64_t* out, int32_t ncta) {
+  SLMM_TRY
+  if (!ms || k < 0 || k >= ms->K || !out) throw std::invalid_argument("bad arguments");
+  auto it = ms->tiles.find(ms->m[k].pattern);
+  if (it == ms->tiles.end() || ncta != it->second.ncta) throw std::invalid_argument("no tiles / wrong CTA count");
+  const QuadTiles& T = it->second;
+  CUDA_OK(cudaDeviceSynchronize());
+  std::vector<long long> cyc = qt_to_host(T.cta_cycles, (size_t)ncta);
+  for (int c = 0; c < ncta; c++) {
+    for (int q = 0; q < 3; q++) out[(size_t)c * 4 + q] = T.cta_stats[(size_t)c * 3 + q];
+    out[(size_t)c * 4 + 3] = cyc[c];
+  }
+  return SLMM_OK;
+  SLMM_CATCH
+}
+
 int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const double* d_X, int32_t ncols, int32_t nb,
                         double* d_dots, double* d_gram_half) {
   SLMM_TRY
@@ -567,10 +625,12 @@ int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
   if (it == ms->tiles.end() || it->second.ntiles == 0) throw std::invalid_argument("build the tiles first (slmm_matset_build_tiles)");
   QuadTiles& T = it->second;
   QtArgs a;
-  a.nentries = T.nentries; a.ndistinct = T.ndistinct; a.ntiles = T.ntiles; a.nrb = T.nrb; a.n = ms->n; a.pad = 0;
+  a.nentries = T.nentries; a.ndistinct = T.ndistinct; a.ntiles = T.ntiles; a.nrb = T.nrb; a.n = ms->n;
+  static const int qt_prefetch = (getenv("SLMM_QT_PREFETCH") && getenv("SLMM_QT_PREFETCH")[0] == '0') ? 0 : 1;
+  a.pad = qt_prefetch;
   a.tile_ptr = T.tile_ptr; a.tile_rb = T.tile_rb; a.tile_dc0 = T.tile_dc0; a.tile_nc = T.tile_nc; a.dcols = T.dcols;
   a.rowid = T.rowid; a.cta_begin = T.cta_begin; a.rowptr = T.rowptr; a.rc = T.rc;
-  a.pair_base = T.pair_base; a.hpairs = T.hpairs;
+  a.pair_base = T.pair_base; a.hpairs = T.hpairs; a.cta_cycles = T.cta_cycles;
   for (int g = 0; g < nk; g++) {
     a.vals[g] = nullptr;
     for (size_t q = 0; q < T.vals_of.size(); q++)

@@ -377,6 +377,13 @@ class MatSet(object):
         check(lib().slmm_matset_tile_stats(self._h, int(k), np_ptr(out)))
         return dict(tiles=int(out[0]), entries=int(out[1]), distinct=int(out[2]), ctas=int(out[3]))
 
+    def tile_cta_profile(self, k):
+        """(ncta, 4) int64: tiles, non-empty rows, entries and clock64 span of every CTA in the last tiled pass."""
+        ncta = self.tile_stats(k)["ctas"]
+        out = np.zeros((ncta, 4), dtype=np.int64)
+        check(lib().slmm_matset_tile_cta_profile(self._h, int(k), np_ptr(out), int(ncta)))
+        return out
+
     def has_tiles(self, ks):
         t = getattr(self, "_tiled", set())
         return all(int(k) in t for k in ks)
