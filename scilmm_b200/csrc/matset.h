@@ -40,6 +40,7 @@ struct QuadTiles {
   int32_t* tile_nc = nullptr;       // [ntiles] columns in the tile (<= 64)
   uint16_t* rowptr = nullptr;       // [ntiles*65] row starts inside the tile
   uint16_t* rc = nullptr;           // [nentries] local column << 1 | diagonal flag
+  uint8_t* roword = nullptr;        // [ntiles*64] rows of a tile by decreasing length, dealt to the 8 warps in snake order (0xFF: none)
   uint32_t* pos = nullptr;          // [nentries] position of the entry in the matrix' own CSR arrays
   int32_t* dcols = nullptr;         // [ndistinct] ORIGINAL row id of the gathered block for every tile column
   int32_t* rowid = nullptr;         // [nrb*64] original row id of every permuted row (-1 past n)
@@ -53,7 +54,7 @@ struct QuadTiles {
   std::vector<double*> vals;        // per matrix of the set sharing this pattern: weighted values in tile order
   std::vector<int> vals_of;         // which matrix each vals[] belongs to
   void release() {
-    dev_free(tile_ptr); dev_free(tile_rb); dev_free(tile_dc0); dev_free(tile_nc); dev_free(rowptr); dev_free(rc);
+    dev_free(tile_ptr); dev_free(tile_rb); dev_free(tile_dc0); dev_free(tile_nc); dev_free(rowptr); dev_free(rc); dev_free(roword); roword = nullptr;
     dev_free(pos); dev_free(dcols); dev_free(rowid); dev_free(cta_begin); dev_free(pair_base); dev_free(pair_rb); dev_free(hpairs); dev_free(cta_cycles); cta_cycles = nullptr;
     pair_base = pair_rb = nullptr; hpairs = nullptr; npairs = 0;
     for (double* v : vals) dev_free(v);

@@ -148,6 +148,7 @@ struct QtArgs {
   double* hpairs;
   long long* cta_cycles;
   const uint16_t *rowptr, *rc;
+  const uint8_t* roword;
   const double* vals[2];
 };
 
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
   double* vS = hbS + QT_RB * G * QT_NB;               // [G][QT_ECAP]  values of the tile's entries
   uint16_t* rcS = reinterpret_cast<uint16_t*>(vS + G * QT_ECAP);      // [QT_ECAP]  local column << 1 | diagonal flag
   __shared__ uint16_t rp_s[QT_RB + 1];
+  __shared__ uint8_t ro_s[QT_RB];                     // row order of the tile: slot s of warp w at [s * 8 + w]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_begin = a.cta_begin[blockIdx.x], t_end = a.cta_begin[blockIdx.x + 1];
   const long long clk0 = clock64();
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     // stage the tile: row starts, entries (if they fit), the nc gathered rows of X
     const bool staged = ne <= QT_ECAP;
     const uint16_t v_rp = tid <= QT_RB ? a.rowptr[(int64_t)t * (QT_RB + 1) + tid] : (uint16_t)0;
+    const uint8_t v_ro = tid < QT_RB ? a.roword[(int64_t)t * QT_RB + tid] : (uint8_t)0;
     int dcv[QT_CH / 8];
 #pragma unroll
     for (int q = 0; q < QT_CH / 8; q++) dcv[q] = (warp + 8 * q < nc) ? a.dcols[dc0 + warp + 8 * q] : -1;
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
       }
     }
     if (tid <= QT_RB) rp_s[tid] = v_rp;
+    if (tid < QT_RB) ro_s[tid] = v_ro;
 #pragma unroll
     for (int q = 0; q < QT_ECAP / 256; q++)
       if (staged && tid + 256 * q < ne) rcS[tid + 256 * q] = v_rc[q];
@@ -232,24 +236,30 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     double nx_v[G];
 #pragma unroll
     for (int g = 0; g < G; g++) nx_v[g] = 0.0;
-    if (!staged) {
-      const int pl = rp_s[warp] + lane;
-      if (pl < rp_s[warp + 1]) {
+    if (!staged && ro_s[warp] != 0xFF) {
+      const int r0 = ro_s[warp];
+      const int pl = rp_s[r0] + lane;
+      if (pl < rp_s[r0 + 1]) {
         nx_rc = (int)a.rc[tb + pl];
 #pragma unroll
         for (int g = 0; g < G; g++) nx_v[g] = __ldcs(a.vals[g] + tb + pl);
       }
     }
-    for (int lr = warp; lr < QT_RB; lr += 8) {
+    // rows by decreasing length, dealt to the warps in snake order at build time: the barrier at the end of the tile
+    // cost 20 % of the warp samples when warp w simply took rows w, w + 8, ...
+    for (int slot = 0; slot < QT_RB / 8; slot++) {
+      const int lr = ro_s[slot * 8 + warp];
+      if (lr == 0xFF) break;                               // the remaining slots of this warp are empty rows
       const int e0 = rp_s[lr], e1 = rp_s[lr + 1];
-      QT_ASSERT(e0 <= e1 && tb + e1 <= a.tile_ptr[t + 1]);
+      QT_ASSERT(e0 < e1 && tb + e1 <= a.tile_ptr[t + 1]);
       const int cur_rc = nx_rc;
       double cur_v[G];
 #pragma unroll
       for (int g = 0; g < G; g++) cur_v[g] = nx_v[g];
-      if (!staged && lr + 8 < QT_RB) {
-        const int pl = rp_s[lr + 8] + lane;
-        const bool in = pl < rp_s[lr + 9];
+      if (!staged && slot + 1 < QT_RB / 8) {
+        const int rn = ro_s[(slot + 1) * 8 + warp];
+        const int pl = rn != 0xFF ? rp_s[rn] + lane : 0;
+        const bool in = rn != 0xFF && pl < rp_s[rn + 1];
         nx_rc = in ? (int)a.rc[tb + pl] : 0;
 #pragma unroll
         for (int g = 0; g < G; g++) nx_v[g] = in ? __ldcs(a.vals[g] + tb + pl) : 0.0;
@@ -546,6 +556,20 @@ int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm,
         while (cta + 1 < ncta && acc >= total * (cta + 1) / ncta) cta_begin[++cta] = t + 1;
       }
       for (int q = cta + 1; q <= ncta; q++) cta_begin[q] = ntiles;
+      // row order of every tile
+      std::vector<uint8_t> roword((size_t)ntiles * QT_RB, 0xFF);
+      for (int t = 0; t < ntiles; t++) {
+        const uint16_t* rp = rptr.data() + (size_t)t * (QT_RB + 1);
+        int idx[QT_RB], cnt = 0;
+        for (int r = 0; r < QT_RB; r++)
+          if (rp[r + 1] > rp[r]) idx[cnt++] = r;
+        std::stable_sort(idx, idx + cnt, [&](int x, int y) { return (rp[x + 1] - rp[x]) > (rp[y + 1] - rp[y]); });
+        for (int p2 = 0; p2 < cnt; p2++) {
+          const int slot = p2 / 8, w = (slot & 1) ? 7 - (p2 % 8) : (p2 % 8);
+          roword[(size_t)t * QT_RB + slot * 8 + w] = (uint8_t)idx[p2];
+        }
+      }
+      T.roword = dev_upload(roword.data(), roword.size());
       T.cta_stats.assign((size_t)ncta * 3, 0);
       for (int c2 = 0; c2 < ncta; c2++)
         for (int t = cta_begin[c2]; t < cta_begin[c2 + 1]; t++) {
@@ -629,7 +653,7 @@ int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
   static const int qt_prefetch = (getenv("SLMM_QT_PREFETCH") && getenv("SLMM_QT_PREFETCH")[0] == '0') ? 0 : 1;
   a.pad = qt_prefetch;
   a.tile_ptr = T.tile_ptr; a.tile_rb = T.tile_rb; a.tile_dc0 = T.tile_dc0; a.tile_nc = T.tile_nc; a.dcols = T.dcols;
-  a.rowid = T.rowid; a.cta_begin = T.cta_begin; a.rowptr = T.rowptr; a.rc = T.rc;
+  a.rowid = T.rowid; a.cta_begin = T.cta_begin; a.rowptr = T.rowptr; a.rc = T.rc; a.roword = T.roword;
   a.pair_base = T.pair_base; a.hpairs = T.hpairs; a.cta_cycles = T.cta_cycles;
   for (int g = 0; g < nk; g++) {
     a.vals[g] = nullptr;
