@@ -530,15 +530,15 @@ int slmm_matset_build_tiles(slmm_matset_t* ms, int32_t k, const int32_t* d_perm,
     for (int i = 0; i < n; i++) rowid[i] = perm[i];
     T.rowid = dev_upload(rowid.data(), rowid.size());
     // static partition of the tiles over the CTAs (two resident per SM) by a cost model in units of one entry:
-    // entries + 20 per non-empty row (a warp exposes the latency of the row's own x_i and of the first entry chunk)
-    // + 400 per tile (metadata, column list, gather: three dependent round trips).  Entries alone left one CTA with
+    // entries + 6 per non-empty row
+    // + 430 per tile (staging round trips, barriers).  Entries alone left one CTA with
     // 25 646 row segments against a mean of 4 632 (the pass took as long as that CTA: 5 of the 6 ms).
     std::vector<int64_t> tptr = qt_to_host(T.tile_ptr, (size_t)ntiles + 1);
     std::vector<uint16_t> rptr = qt_to_host(T.rowptr, (size_t)ntiles * (QT_RB + 1));
     const int ncta = std::max(1, std::min(148 * 2, ntiles));
     std::vector<int32_t> cta_begin(ncta + 1, ntiles);
     {
-      const double per_tile = 400.0, per_row = 20.0;
+      const double per_tile = 430.0, per_row = 6.0;      // least-squares fit of per-CTA cycle counts (scripts/tile_profile.py)
       std::vector<double> cost((size_t)ntiles);
       double total = 0;
       for (int t = 0; t < ntiles; t++) {

@@ -681,3 +681,19 @@ def test_upload_columns_pitched_copy(eng):
         eng.upload_columns(np.asfortranarray(Z), 0, 3)
     with pytest.raises(ValueError):
         eng.upload_columns(Z.astype(np.float32), 0, 3)
+
+
+def test_symmetry_detection_by_hash_sums(golden_c1mini, eng):
+    """MatSet.is_symmetric (one streaming pass of hash sums): symmetric matrices pass; a single off-diagonal value
+    changed in its last bit, a single missing mirror entry, and a pair of swapped values are all recognised."""
+    g = golden_c1mini
+    A = g.csr("A")
+    B = A.copy(); C_ = A.copy(); D = A.copy()
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    off = np.flatnonzero(rows != A.indices)
+    B.data[off[5]] = np.nextafter(B.data[off[5]], 2.0)
+    C_.data[off[7]] = 0.0; C_.eliminate_zeros()
+    up = off[rows[off] < A.indices[off]]
+    D.data[up[0]], D.data[up[1]] = D.data[up[1]] + 0.25, D.data[up[0]] + 0.25
+    ms = eng.MatSet([A, B, C_.tocsr(), D])
+    assert ms.is_symmetric(0) and not ms.is_symmetric(1) and not ms.is_symmetric(2) and not ms.is_symmetric(3)
