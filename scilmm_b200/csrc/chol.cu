@@ -320,8 +320,6 @@ struct Schedule {
   double* d_ws = nullptr;
   double* d_ws2 = nullptr;
   ReduceOp* d_reduce = nullptr;
-  int64_t ncounters = 0;          // arrival counters of the split-K parts reduced inside the narrow-RHS kernels
-  int* d_counters = nullptr;
   GemmOp* d_gemm = nullptr;
   PotrfOp* d_potrf = nullptr;
   PullItem* d_pull = nullptr;
@@ -344,10 +342,6 @@ struct Schedule {
       }
     }
     d_reduce = dev_upload(reduce.data(), reduce.size());
-    if (ncounters > 0) {
-      d_counters = dev_alloc<int>((size_t)ncounters);
-      CUDA_OK(cudaMemset(d_counters, 0, (size_t)ncounters * sizeof(int)));
-    }
     d_gemm = dev_upload(gemm.data(), gemm.size());
     d_potrf = dev_upload(potrf.data(), potrf.size());
     d_pull = dev_upload(pull.data(), pull.size());
@@ -360,7 +354,6 @@ struct Schedule {
     dev_free(d_gemm); dev_free(d_potrf); dev_free(d_pull); dev_free(d_ws); dev_free(d_ws2); dev_free(d_reduce); dev_free(d_tile_op); dev_free(d_pull_entries);
     d_ws2 = nullptr;
     dev_free(d_tmaps); d_tmaps = nullptr;
-    dev_free(d_counters); d_counters = nullptr;
     d_tile_op = nullptr; d_pull_entries = nullptr;
     d_gemm = nullptr; d_potrf = nullptr; d_pull = nullptr; d_ws = nullptr; d_reduce = nullptr;
   }
@@ -378,7 +371,6 @@ struct PhaseBuilder {
   int ws_id = 0;                              // which split-K workspace this builder's partial products use
   std::vector<PotrfOp> potrf;
   std::vector<ReduceOp> reduces;
-  std::vector<ReduceOp> fused;                // split-K reductions done by the last-arriving CTA of a narrow-RHS kernel
   int64_t ws_used = 0;
   bool allow_split = true;    // builders whose launches run beside another builder's must not share the split-K workspace
   static bool tma_ok(const GemmOp& op) {
@@ -417,11 +409,6 @@ struct PhaseBuilder {
     }
     ws_used += (int64_t)S * mn;
   }
-  static bool fuse_reduce() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("SLMM_FUSE_REDUCE"); on = (e && e[0] == '0') ? 0 : 1; }
-    return on == 1;
-  }
   bool add_skinny(const GemmOp& op) {
     if (skinny_mt <= 0 || op.M > skinny_mt || op.a_si != 1 || op.c_si != 1 || (op.flags & (GF_LOWER | GF_BIGTILE))) return false;
     const bool f1 = op.b_sj == 1 && op.a_kidx == nullptr;
@@ -444,16 +431,8 @@ struct PhaseBuilder {
       if (!f1) kc = std::min(kc, SK_F2_KMAX);
       S = (op.K + kc - 1) / kc;
     }
-    if (S <= 1) { GemmOp o = op; o.pad = 0; o.tiles_m = 0; dst.push_back(o); }
-    else if (fuse_reduce()) {
-      // the reduction of the S partial products happens inside the kernel (skinny_ops.cuh): no reduce launch
-      split_k(op, S, kc, [&](const GemmOp& part) { dst.push_back(part); });
-      ReduceOp r = reduces.back();
-      reduces.pop_back();
-      r.pad = (int32_t)nj;                                 // arrival counters: one per block of output columns
-      fused.push_back(r);
-      for (size_t q = dst.size() - S; q < dst.size(); q++) dst[q].tiles_m = (int32_t)fused.size();   // index + 1
-    } else split_k(op, S, kc, [&](const GemmOp& part) { GemmOp o = part; o.tiles_m = 0; dst.push_back(o); });
+    if (S <= 1) { GemmOp o = op; o.pad = 0; dst.push_back(o); }
+    else split_k(op, S, kc, [&](const GemmOp& part) { dst.push_back(part); });
     return true;
   }
   void add(GemmOp op) {
@@ -543,16 +522,6 @@ struct PhaseBuilder {
       sch.launches.push_back(L);
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
-    int64_t fused_off = 0;
-    if (!fused.empty()) {
-      fused_off = (int64_t)sch.reduce.size();
-      for (ReduceOp& r : fused) {
-        r.block_start = (int32_t)sch.ncounters;            // first arrival counter of this reduction
-        sch.ncounters += r.pad;
-      }
-      sch.reduce.insert(sch.reduce.end(), fused.begin(), fused.end());
-      if (ws_id) sch.ws2_size = std::max(sch.ws2_size, ws_used); else sch.ws_size = std::max(sch.ws_size, ws_used);
-    }
     for (int pass = 0; pass < 2; pass++) {      // narrow-RHS streaming flavours: one CTA per block of output columns
       std::vector<GemmOp>& v = pass == 0 ? sk1 : sk2;
       if (v.empty()) continue;
@@ -560,7 +529,8 @@ struct PhaseBuilder {
       int64_t tiles = 0;
       double lf = 0;
       for (GemmOp& op : v) {
-        op.tiles_n = (op.N + T - 1) / T;                  // tiles_m: index + 1 of the fused reduction (0: none)
+        op.tiles_m = 1;
+        op.tiles_n = (op.N + T - 1) / T;
         op.tile_start = (int32_t)tiles;
         tiles += op.tiles_n;
         const double f = (op.flags & GF_TRIL_B) ? (double)op.M * op.N * op.K : 2.0 * op.M * op.N * op.K;
@@ -573,10 +543,8 @@ struct PhaseBuilder {
       for (size_t q = 0; q < v.size(); q++)
         std::fill(sch.tile_op.begin() + tile_off + v[q].tile_start,
                   sch.tile_op.begin() + tile_off + v[q].tile_start + v[q].tiles_n, (int32_t)q);
-      Launch L{pass == 0 ? Launch::SKINNY_F1 : Launch::SKINNY_F2, (int64_t)sch.gemm.size(),
-               (int32_t)v.size(), (int32_t)tiles, skinny_mt, lf, tile_off};
-      L.aux_off = fused_off;
-      sch.launches.push_back(L);
+      sch.launches.push_back({pass == 0 ? Launch::SKINNY_F1 : Launch::SKINNY_F2, (int64_t)sch.gemm.size(),
+                              (int32_t)v.size(), (int32_t)tiles, skinny_mt, lf, tile_off});
       sch.gemm.insert(sch.gemm.end(), v.begin(), v.end());
     }
     if (!reduces.empty()) {
@@ -590,7 +558,7 @@ struct PhaseBuilder {
       if (ws_id) sch.ws2_size = std::max(sch.ws2_size, ws_used); else sch.ws_size = std::max(sch.ws_size, ws_used);
     }
     for (size_t q = first_launch; q < sch.launches.size(); q++) sch.launches[q].stream = stream;
-    big.clear(); small.clear(); tma.clear(); sk1.clear(); sk2.clear(); potrf.clear(); reduces.clear(); fused.clear();
+    big.clear(); small.clear(); tma.clear(); sk1.clear(); sk2.clear(); potrf.clear(); reduces.clear();
     ws_used = 0;
   }
   bool empty() const { return big.empty() && small.empty() && tma.empty() && sk1.empty() && sk2.empty() && potrf.empty(); }
@@ -724,8 +692,8 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       const int32_t* top = sch.d_tile_op + L.tile_off;
       const bool f1 = L.kind == Launch::SKINNY_F1;
 #define SK_CASE(MT)                                                                                          \
-  if (f1) skinny_f1_kernel<MT><<<L.grid, SK_F1_COLS, 0, st>>>(ops, top, sch.d_reduce + L.aux_off, sch.d_counters);   \
-  else skinny_f2_kernel<MT><<<L.grid, 256, SK_F2_KMAX * MT * sizeof(double), st>>>(ops, top, sch.d_reduce + L.aux_off, sch.d_counters);
+  if (f1) skinny_f1_kernel<MT><<<L.grid, SK_F1_COLS, 0, st>>>(ops, top);                                     \
+  else skinny_f2_kernel<MT><<<L.grid, 256, SK_F2_KMAX * MT * sizeof(double), st>>>(ops, top);
       switch (L.child_parity) {
         case 1: SK_CASE(1) break;
         case 2: SK_CASE(2) break;

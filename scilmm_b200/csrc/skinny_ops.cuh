@@ -24,28 +24,9 @@ constexpr int SK_F1_KC = 256;      // k chunk staged in shared memory per pass
 constexpr int SK_F2_COLS = 64;     // output columns per CTA, flavour 2 (8 warps x 8 columns)
 constexpr int SK_F2_KMAX = 512;    // an F2 work item holds its whole K range of A in shared memory
 
-// Arrival counter of a block of output columns shared by the S split-K parts: true in every thread of the CTA that
-// arrives last (its partial and everyone else's are then visible); that CTA also re-arms the counter for the next
-// replay of the schedule.
-__device__ __forceinline__ bool skinny_last_arrival(int* counter, int S) {
-  __shared__ int last_s;
-  __threadfence();                                   // this CTA's partial products before its ticket
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(counter, 1);
-    last_s = ticket == S - 1;
-    if (last_s) *counter = 0;
-  }
-  __syncthreads();
-  const bool last = last_s != 0;
-  if (last) __threadfence();
-  return last;
-}
-
 template <int MT>
 __global__ void __launch_bounds__(SK_F1_COLS) skinny_f1_kernel(const GemmOp* __restrict__ ops,
-                                                               const int32_t* __restrict__ tile_op,
-                                                               const ReduceOp* __restrict__ reds, int* __restrict__ counters) {
+                                                               const int32_t* __restrict__ tile_op) {
   __shared__ double As[SK_F1_KC * MT];                 // [k][i]
   const int tile = blockIdx.x;
   const GemmOp& op = ops[tile_op[tile]];
@@ -114,40 +95,20 @@ __global__ void __launch_bounds__(SK_F1_COLS) skinny_f1_kernel(const GemmOp* __r
       for (int i = 0; i < MT; i++) acc[i] += As[k * MT + i] * b;
     }
   }
-  if (active) {
-    double* c = op.C + (int64_t)j * op.c_sj;
-    const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG;
+  if (!active) return;
+  double* c = op.C + (int64_t)j * op.c_sj;
+  const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG;
 #pragma unroll
-    for (int i = 0; i < MT; i++)
-      if (i < M) {
-        const double v = neg ? -acc[i] : acc[i];
-        c[i] = accum ? c[i] + v : v;
-      }
-  }
-  if (op.tiles_m > 0) {
-    // split-K part: the partial product above went to the workspace; the LAST part of this block of columns to
-    // arrive adds the S partials in part order (the sum does not depend on which CTA that is) and applies them
-    const ReduceOp& r = reds[op.tiles_m - 1];
-    if (skinny_last_arrival(counters + r.block_start + (tile - op.tile_start), r.S) && active) {
-      const int64_t mn = (int64_t)r.M * r.N;
-      const double* w = r.ws + (int64_t)j * r.M;
-      double* c = r.C + (int64_t)j * r.c_sj;
-#pragma unroll
-      for (int i = 0; i < MT; i++)
-        if (i < M) {
-          double sum = 0.0;
-          for (int q = 0; q < r.S; q++) sum += __ldcg(w + (int64_t)q * mn + i);
-          const double v = (r.flags & GF_NEG) ? -sum : sum;
-          c[(int64_t)i * r.c_si] = (r.flags & GF_ACCUM) ? c[(int64_t)i * r.c_si] + v : v;
-        }
+  for (int i = 0; i < MT; i++)
+    if (i < M) {
+      const double v = neg ? -acc[i] : acc[i];
+      c[i] = accum ? c[i] + v : v;
     }
-  }
 }
 
 template <int MT>
 __global__ void __launch_bounds__(256, 2) skinny_f2_kernel(const GemmOp* __restrict__ ops,
-                                                           const int32_t* __restrict__ tile_op,
-                                                           const ReduceOp* __restrict__ reds, int* __restrict__ counters) {
+                                                        const int32_t* __restrict__ tile_op) {
   extern __shared__ double As2[];                      // [i][K] (lanes read consecutive k: conflict free)
   const int tile = blockIdx.x;
   const GemmOp& op = ops[tile_op[tile]];
@@ -231,22 +192,6 @@ __global__ void __launch_bounds__(256, 2) skinny_f2_kernel(const GemmOp* __restr
         double* c1 = op.C + lane + (int64_t)j1c * op.c_sj;
         const double v1 = neg ? -m1 : m1;
         *c1 = accum ? *c1 + v1 : v1;
-      }
-    }
-  }
-  if (op.tiles_m > 0) {                                // split-K part: see skinny_f1_kernel
-    const ReduceOp& r = reds[op.tiles_m - 1];
-    if (skinny_last_arrival(counters + r.block_start + (tile - op.tile_start), r.S)) {
-      const int64_t mn = (int64_t)r.M * r.N;
-      const int ncol = min(SK_F2_COLS, N - j0);
-      for (int e = threadIdx.x; e < ncol * M; e += 256) {
-        const int jj = e / M, i = e - jj * M;
-        const double* w = r.ws + (int64_t)(j0 + jj) * r.M + i;
-        double sum = 0.0;
-        for (int q = 0; q < r.S; q++) sum += __ldcg(w + (int64_t)q * mn);
-        double* c = r.C + (int64_t)i * r.c_si + (int64_t)(j0 + jj) * r.c_sj;
-        const double v = (r.flags & GF_NEG) ? -sum : sum;
-        *c = (r.flags & GF_ACCUM) ? *c + v : v;
       }
     }
   }
