@@ -10,6 +10,7 @@
 #include <numeric>
 #include <cstdio>
 #include <stdexcept>
+#include <thread>
 
 extern "C" int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
                             int64_t* perm, int64_t* iperm);
@@ -176,29 +177,87 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
 // No sorting: the pattern is symmetric, so the permuted matrix equals its transpose, and a transpose built by walking
 // the new rows i = 0..n-1 in order and appending i to the list of every new column j it touches comes out with
 // sorted lists (one counting pass + one scatter pass over the entries instead of 6e7 entries of std::sort).
+static int host_threads() {
+  int T = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("SLMM_HOST_THREADS")) T = atoi(e);
+  return std::max(1, std::min(T, 32));
+}
+
 void permute_pattern(int n, const int32_t* ap, const int32_t* ai, const std::vector<int32_t>& perm,
                      const std::vector<int32_t>& iperm, std::vector<int64_t>& bp, std::vector<int32_t>& bi) {
   bp.assign(n + 1, 0);
   for (int i = 0; i < n; i++) {            // by symmetry the list of new column i is as long as new row i
-    int o = perm[i];
+    const int o = perm[i];
     int64_t c = 0;
     for (int p = ap[o]; p < ap[o + 1]; p++)
       if (ai[p] != o) c++;
     bp[i + 1] = bp[i] + c;
   }
   bi.resize(bp[n]);
-  std::vector<int64_t> fill(bp.begin(), bp.end() - 1);
-  for (int i = 0; i < n; i++) {
-    int o = perm[i];
-    for (int p = ap[o]; p < ap[o + 1]; p++) {
-      if (ai[p] == o) continue;
-      const int j = iperm[ai[p]];
-      if (fill[j] >= bp[j + 1]) throw std::runtime_error("the pattern is not structurally symmetric");
-      bi[fill[j]++] = i;
+  const int T = (bp[n] < ((int64_t)1 << 20) && !getenv("SLMM_HOST_THREADS")) ? 1 : host_threads();
+  if (T < 6) {
+    // few cores: one counting pass + one scatter pass, rows taken in new order so every list comes out sorted.  The
+    // scatter writes one cache line per entry (memory bound: it does not speed up with threads).
+    std::vector<int64_t> fill(bp.begin(), bp.end() - 1);
+    for (int i = 0; i < n; i++) {
+      const int o = perm[i];
+      for (int p = ap[o]; p < ap[o + 1]; p++) {
+        if (ai[p] == o) continue;
+        const int j = iperm[ai[p]];
+        if (fill[j] >= bp[j + 1]) throw std::runtime_error("the pattern is not structurally symmetric");
+        bi[fill[j]++] = i;
+      }
     }
+    for (int j = 0; j < n; j++)
+      if (fill[j] != bp[j + 1]) throw std::runtime_error("the pattern is not structurally symmetric");
+    return;
   }
-  for (int j = 0; j < n; j++)
-    if (fill[j] != bp[j + 1]) throw std::runtime_error("the pattern is not structurally symmetric");
+  // many cores: by symmetry the list of new column j is the neighbour list of the original vertex perm[j],
+  // relabelled and sorted; columns are independent, threads take column ranges of equal entry counts (sequential
+  // reads, cache-resident sorts, sequential writes: 3.9 s on one core, 0.8 s on 8, against 1.05 s for the scatter).
+  // Structural symmetry, which this construction relies on, is verified with order-independent hash sums of the
+  // entries above / below the diagonal under the key (min, max): equal totals <=> every (i, j) has its (j, i).
+  std::vector<int> bad(T, 0);
+  std::vector<uint64_t> hup(T, 0), hlo(T, 0);
+  auto mix = [](uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+  };
+  auto work = [&](int t) {
+    const int64_t lo = bp[n] * t / T, hi = bp[n] * (t + 1) / T;
+    const int j0 = (int)(std::lower_bound(bp.begin(), bp.end(), lo) - bp.begin());
+    const int j1 = t + 1 == T ? n : (int)(std::lower_bound(bp.begin(), bp.end(), hi) - bp.begin());
+    uint64_t up = 0, lw = 0;
+    for (int j = j0; j < j1; j++) {
+      const int o = perm[j];
+      int32_t* dst = bi.data() + bp[j];
+      int64_t c = 0;
+      for (int p = ap[o]; p < ap[o + 1]; p++)
+        if (ai[p] != o) dst[c++] = iperm[ai[p]];
+      std::sort(dst, dst + c);
+      for (int64_t q = 0; q < c; q++) {
+        if (q > 0 && dst[q] == dst[q - 1]) bad[t] = 1;         // duplicate entries in a row
+        const uint32_t i = (uint32_t)dst[q];
+        const uint64_t h = mix(((uint64_t)std::min<uint32_t>(i, (uint32_t)j) << 32) | std::max<uint32_t>(i, (uint32_t)j));
+        if ((int)i > j) up += h; else lw += h;
+      }
+    }
+    hup[t] = up;
+    hlo[t] = lw;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  uint64_t su = 0, sl = 0;
+  for (int t = 0; t < T; t++) {
+    if (bad[t]) throw std::runtime_error("duplicate entries in the pattern");
+    su += hup[t];
+    sl += hlo[t];
+  }
+  if (su != sl) throw std::runtime_error("the pattern is not structurally symmetric");
 }
 
 // elimination tree of the permuted matrix straight from the original pattern (Liu's algorithm needs the entries of a
@@ -352,9 +411,13 @@ void analyze(int n, const int32_t* ap, const int32_t* ai, const int32_t* user_pe
     for (int i = 0; i < n; i++) S.iperm[S.perm[i]] = i;
     permute_pattern(n, ap, ai, S.perm, S.iperm, bp, bi);
     lap("permute_pattern #2");
-    etree(n, bp, bi, S.parent);
+    // the tree of the postordered matrix is the first tree relabelled (a postorder is an equivalent reordering)
+    std::vector<int32_t> ipost(n);
+    for (int k = 0; k < n; k++) ipost[post[k]] = k;
+    S.parent.assign(n, -1);
+    for (int k = 0; k < n; k++) S.parent[k] = par0[post[k]] == -1 ? -1 : ipost[par0[post[k]]];
     is_post = true;
-    lap("etree #2");
+    lap("etree #2 (relabelled)");
   }
   if (is_post) {
     column_counts(n, bp, bi, S.parent, S.colcount);

@@ -224,3 +224,38 @@ def test_cpu_supernodal_oracle_on_the_engine_plan(case, tag, request):
     assert np.max(np.abs(f(b) - d(b))) < 1e-11 * np.max(np.abs(d(b)))
     assert abs(f.L() - d.L()).max() < 1e-12
     assert np.max(np.abs(f.lmul_unperm(b) - d.L().dot(b)[np.argsort(d.P())])) < 1e-11
+
+
+def test_threaded_pattern_permutation_matches_the_sequential_one():
+    """csrc/symbolic.cpp permute_pattern has two formulations (sequential counting scatter; per-column gather + sort
+    on host threads, chosen on machines with >= 6 cores): the whole analysis must come out identical, and the
+    threaded one must refuse a structurally asymmetric pattern like the sequential one does."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, scipy.sparse as sp, hashlib
+        sys.path.insert(0, %r)
+        from scilmm_b200 import engine as E
+        rng = np.random.default_rng(5)
+        n = 6000
+        B = sp.random(n, n, density=0.004, random_state=3, format='csr')
+        A = (B + B.T + sp.eye(n)).tocsr(); A.data[:] = 1.0
+        a = E.SymbolicView(A, ordering='metis').arrays()
+        h = hashlib.sha256()
+        for k in ('perm', 'parent', 'colcount', 'sn_first', 'sn_nrow', 'rows', 'rel', 'level_sn'):
+            h.update(np.ascontiguousarray(a[k]).tobytes())
+        print('HASH', h.hexdigest())
+        U = sp.triu(A, 1).tolil(); U[3, 4000] = 1.0
+        bad = (sp.tril(A) + U.tocsr()).tocsr()
+        try:
+            E.SymbolicView(bad, ordering='metis')
+            print('ASYM accepted')
+        except Exception as e:
+            print('ASYM', 'symmetric' in str(e))
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for t in ("1", "8"):
+        env = dict(os.environ, SLMM_HOST_THREADS=t)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith(("HASH", "ASYM"))])
+    assert outs[0] == outs[1] and outs[0][0].startswith("HASH") and outs[0][1] == "ASYM True", outs
