@@ -229,8 +229,6 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
-    // column list of the NEXT tile: its gathered rows of X are pulled into L2 while this tile computes
-    const int dnext = ((a.pad & 1) && t + 1 < t_end && tid < nc_n) ? a.dcols[dc0_n + tid] : -1;
     // first entry chunk of the warp's next row, fetched one row ahead (tiles too large for the staging buffer)
     int nx_rc = 0;
     double nx_v[G];
@@ -309,10 +307,6 @@ __global__ void __launch_bounds__(256, 2) quadform_tiled_kernel(QtArgs a, const 
 #pragma unroll
         for (int g = 0; g < G; g++) hbS[(lr * G + g) * QT_NB + lane] += acc[g][0];
       }
-    }
-    if (dnext >= 0) {
-      const char* pf = reinterpret_cast<const char*>(X + (int64_t)dnext * ncx);
-      for (int b = 0; b < ncx * 8; b += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf + b));
     }
     __syncthreads();
     // end of the row block (or of this CTA's range): park the narrow-block row products of this (CTA, row block)
@@ -649,9 +643,7 @@ int slmm_quadform_tiled(slmm_matset_t* ms, int32_t nk, const int32_t* ks, const 
   if (it == ms->tiles.end() || it->second.ntiles == 0) throw std::invalid_argument("build the tiles first (slmm_matset_build_tiles)");
   QuadTiles& T = it->second;
   QtArgs a;
-  a.nentries = T.nentries; a.ndistinct = T.ndistinct; a.ntiles = T.ntiles; a.nrb = T.nrb; a.n = ms->n;
-  static const int qt_prefetch = (getenv("SLMM_QT_PREFETCH") && getenv("SLMM_QT_PREFETCH")[0] == '0') ? 0 : 1;
-  a.pad = qt_prefetch;
+  a.nentries = T.nentries; a.ndistinct = T.ndistinct; a.ntiles = T.ntiles; a.nrb = T.nrb; a.n = ms->n; a.pad = 0;
   a.tile_ptr = T.tile_ptr; a.tile_rb = T.tile_rb; a.tile_dc0 = T.tile_dc0; a.tile_nc = T.tile_nc; a.dcols = T.dcols;
   a.rowid = T.rowid; a.cta_begin = T.cta_begin; a.rowptr = T.rowptr; a.rc = T.rc; a.roword = T.roword;
   a.pair_base = T.pair_base; a.hpairs = T.hpairs; a.cta_cycles = T.cta_cycles;
