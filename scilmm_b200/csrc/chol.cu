@@ -653,6 +653,8 @@ static void init_kernel_attributes() {
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
   CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 12 * 8));
   CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 16 * 8));
+  CUDA_OK(cudaFuncSetAttribute(skinny_f2_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SK_F2D_KP * 8));
+  CUDA_OK(cudaFuncSetAttribute(skinny_f2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SK_F2D_KP * 8));
   done = true;
 }
 
@@ -691,6 +693,18 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       const GemmOp* ops = sch.d_gemm + L.off;
       const int32_t* top = sch.d_tile_op + L.tile_off;
       const bool f1 = L.kind == Launch::SKINNY_F1;
+      static const bool f2_dmma = !(getenv("SLMM_F2_DMMA") && getenv("SLMM_F2_DMMA")[0] == '0');
+      static const bool f1_dmma = !(getenv("SLMM_F1_DMMA") && getenv("SLMM_F1_DMMA")[0] == '0');
+      if (f1 && f1_dmma && L.child_parity >= 8) {        // 5..16 right-hand sides: forward flavour on the tensor pipe
+        if (L.child_parity == 8) skinny_f1_dmma_kernel<1><<<L.grid, 256, 0, st>>>(ops, top);
+        else skinny_f1_dmma_kernel<2><<<L.grid, 256, 0, st>>>(ops, top);
+        break;
+      }
+      if (!f1 && f2_dmma && L.child_parity >= 8) {       // 5..16 right-hand sides: backward flavour on the tensor pipe
+        if (L.child_parity == 8) skinny_f2_dmma_kernel<1><<<L.grid, 256, 8 * SK_F2D_KP * sizeof(double), st>>>(ops, top);
+        else skinny_f2_dmma_kernel<2><<<L.grid, 256, 16 * SK_F2D_KP * sizeof(double), st>>>(ops, top);
+        break;
+      }
 #define SK_CASE(MT)                                                                                          \
   if (f1) skinny_f1_kernel<MT><<<L.grid, SK_F1_COLS, 0, st>>>(ops, top);                                     \
   else skinny_f2_kernel<MT><<<L.grid, 256, SK_F2_KMAX * MT * sizeof(double), st>>>(ops, top);

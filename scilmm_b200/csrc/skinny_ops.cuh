@@ -197,4 +197,198 @@ __global__ void __launch_bounds__(256, 2) skinny_f2_kernel(const GemmOp* __restr
   }
 }
 
+// Backward-sweep flavour on the FP64 tensor pipe, for 5..16 right-hand sides.  Same tiling and operand staging as
+// skinny_f2_kernel (64 output columns per CTA, A(M x K <= 512) in shared memory), but the products run as DMMA
+// m8n8k4: a warp owns 8 output columns, its B fragment b[k = t][n = g] = B(j0 + g, kk + t) comes STRAIGHT from global
+// memory (each lane 8 bytes, a quad 32 contiguous bytes of one column of L: whole sectors, 256 bytes per warp load
+// like a coalesced load), the A fragments from shared memory (leading dimension = 4 mod 16: conflict free).  The
+// register-blocked kernel reads 12..16 shared-memory values per pair of streamed values and is bound by that; here it
+// is 2 per streamed value and the FMA work leaves the FP64 pipe.  NMT = row tiles of 8 (1: M <= 8, 2: M <= 16).
+constexpr int SK_F2D_KP = SK_F2_KMAX + 4;          // padded leading dimension of the staged operand
+
+template <int NMT>
+__global__ void __launch_bounds__(256, 3) skinny_f2_dmma_kernel(const GemmOp* __restrict__ ops,
+                                                                const int32_t* __restrict__ tile_op) {
+  extern __shared__ double Ad[];                       // [8 * NMT][KP], zero beyond (M, K)
+  const int tile = blockIdx.x;
+  const GemmOp& op = ops[tile_op[tile]];
+  const int j0 = (tile - op.tile_start) * SK_F2_COLS;
+  const int M = op.M, N = op.N, K = op.K, flags = op.flags;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int K4 = (K + 3) & ~3;
+  const int KP = ((K4 + 15) & ~15) + 4;
+  const int32_t* __restrict__ kidx = op.a_kidx;
+  {
+    const int64_t a_sk = op.a_sk;
+    const int total = K * M;
+    for (int q0 = threadIdx.x; q0 < total; q0 += 4 * 256) {
+      double v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = q0 + u * 256;
+        const int k = q / M, i = q - k * M;
+        dst[u] = q < total ? i * KP + k : -1;
+        v[u] = q < total ? op.A[(int64_t)i + (int64_t)(kidx ? kidx[k] : k) * a_sk] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (dst[u] >= 0) Ad[dst[u]] = v[u];
+    }
+    // zero padding: rows M..8*NMT over [0, K4) and the k tail [K, K4) of the live rows
+    for (int q = threadIdx.x; q < (8 * NMT - M) * K4; q += 256) Ad[(M + q / K4) * KP + q % K4] = 0.0;
+    if (K4 > K)
+      for (int q = threadIdx.x; q < M * (K4 - K); q += 256) Ad[(q / (K4 - K)) * KP + K + q % (K4 - K)] = 0.0;
+  }
+  __syncthreads();
+  const int jb = j0 + 8 * warp;                        // this warp's 8 output columns
+  if (jb >= N) return;
+  const int jg = min(jb + g, N - 1);                   // clamped: columns past N are computed and dropped
+  const double* __restrict__ Bg = op.B + (int64_t)jg * op.b_sj + t;
+  const double* a0 = Ad + g * KP + t;
+  double d[NMT][2];
+#pragma unroll
+  for (int m = 0; m < NMT; m++) d[m][0] = d[m][1] = 0.0;
+  int kk = 0;
+  for (; kk + 32 <= K; kk += 32) {                     // 8 independent 8-byte loads in flight per lane
+    double b[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) b[u] = __ldcs(Bg + kk + 4 * u);
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int m = 0; m < NMT; m++) dmma884(d[m][0], d[m][1], a0[m * 8 * KP + kk + 4 * u], b[u]);
+  }
+  for (; kk < K4; kk += 4) {
+    const double b = (kk + t < K) ? __ldcs(Bg + kk) : 0.0;
+#pragma unroll
+    for (int m = 0; m < NMT; m++) dmma884(d[m][0], d[m][1], a0[m * 8 * KP + kk], b);
+  }
+  const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG;
+#pragma unroll
+  for (int m = 0; m < NMT; m++) {
+    const int i = 8 * m + g;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int j = jb + 2 * t + h;
+      if (i < M && j < N) {
+        double* c = op.C + (int64_t)i * op.c_si + (int64_t)j * op.c_sj;
+        const double v = neg ? -d[m][h] : d[m][h];
+        *c = accum ? *c + v : v;
+      }
+    }
+  }
+}
+
+// Forward flavour on the FP64 tensor pipe (5..16 right-hand sides): B(j, k) = B[j + k*b_sk], a warp owns 16 output
+// columns (two 8-column DMMA tiles); its B fragment b[k = t][n = g] = B(jb + g, kk + t) comes straight from global
+// memory - for a fixed k the 8 lanes of a g-group read 64 contiguous bytes, the 8 warps of a CTA 1 KB of that k-row.
+// A(M x K) is staged in K chunks of 256 as [i][260] (leading dimension = 4 mod 16: conflict-free fragment reads).
+// Same op lists, tiling (128 columns per CTA) and split-K parts as skinny_f1_kernel.
+constexpr int SK_F1D_KCP = SK_F1_KC + 4;
+
+template <int NMT>
+__global__ void __launch_bounds__(256, 3) skinny_f1_dmma_kernel(const GemmOp* __restrict__ ops,
+                                                                const int32_t* __restrict__ tile_op) {
+  __shared__ double As[8 * NMT * SK_F1D_KCP];
+  const int tile = blockIdx.x;
+  const GemmOp& op = ops[tile_op[tile]];
+  const int jt0 = (tile - op.tile_start) * SK_F1_COLS;
+  const int M = op.M, N = op.N, K = op.K, flags = op.flags;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const bool tril = flags & GF_TRIL_B;
+  // lower-triangular B (L11 of L*Z): B(j,k) = 0 for k > j; op.pad = first k of this (split) part
+  const int kend = tril ? min(K, max(0, min(N - 1, jt0 + SK_F1_COLS - 1) + 1 - op.pad)) : K;
+  const int jb = jt0 + 16 * warp;
+  const bool wactive = jb < N;
+  const int jc0 = min(jb + g, N - 1), jc1 = min(jb + 8 + g, N - 1);      // clamped: columns past N are dropped
+  const int64_t b_sk = op.b_sk;
+  const double* __restrict__ B0 = op.B + jc0 + (int64_t)t * b_sk;
+  const double* __restrict__ B1 = op.B + jc1 + (int64_t)t * b_sk;
+  const int kw = tril ? min(kend, max(0, min(N - 1, jb + 15) + 1 - op.pad)) : kend;     // this warp's own k bound
+  const int lim0 = tril ? jc0 - op.pad : K, lim1 = tril ? jc1 - op.pad : K;              // entries with k > lim are zero
+  double d[NMT][2][2];
+#pragma unroll
+  for (int m = 0; m < NMT; m++) d[m][0][0] = d[m][0][1] = d[m][1][0] = d[m][1][1] = 0.0;
+  const double* a0 = As + g * SK_F1D_KCP + t;
+  for (int k0 = 0; k0 < kend; k0 += SK_F1_KC) {
+    const int kc = min(SK_F1_KC, kend - k0), kc4 = (kc + 3) & ~3;
+    __syncthreads();
+    {
+      const int total = kc * M;
+      const double* __restrict__ Ab = op.A + (int64_t)k0 * op.a_sk;
+      const int64_t a_sk = op.a_sk;
+      for (int q0 = threadIdx.x; q0 < total; q0 += 4 * 256) {
+        double v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int q = q0 + u * 256;
+          const int k = q / M, i = q - k * M;
+          dst[u] = q < total ? i * SK_F1D_KCP + k : -1;
+          v[u] = q < total ? Ab[(int64_t)k * a_sk + i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (dst[u] >= 0) As[dst[u]] = v[u];
+      }
+      for (int q = threadIdx.x; q < (8 * NMT - M) * kc4; q += 256) As[(M + q / kc4) * SK_F1D_KCP + q % kc4] = 0.0;
+      if (kc4 > kc)
+        for (int q = threadIdx.x; q < M * (kc4 - kc); q += 256) As[(q / (kc4 - kc)) * SK_F1D_KCP + kc + q % (kc4 - kc)] = 0.0;
+    }
+    __syncthreads();
+    if (!wactive) continue;
+    const int kl = min(kc, kw - k0);                   // k range of this chunk this warp needs
+    int kk = 0;
+    for (; kk + 16 <= kl; kk += 16) {                  // 4 k-steps x 2 column tiles: 8 independent loads per lane
+      double b0[4], b1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int kg = k0 + kk + 4 * u + t;
+        b0[u] = kg <= lim0 ? __ldcs(B0 + (int64_t)(k0 + kk + 4 * u) * b_sk) : 0.0;
+        b1[u] = kg <= lim1 ? __ldcs(B1 + (int64_t)(k0 + kk + 4 * u) * b_sk) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int m = 0; m < NMT; m++) {
+          const double a = a0[m * 8 * SK_F1D_KCP + kk + 4 * u];
+          dmma884(d[m][0][0], d[m][0][1], a, b0[u]);
+          dmma884(d[m][1][0], d[m][1][1], a, b1[u]);
+        }
+    }
+    for (; kk < kl; kk += 4) {
+      const int kg = k0 + kk + t;
+      const bool in = kk + t < kc;
+      const double b0 = (in && kg <= lim0) ? __ldcs(B0 + (int64_t)(k0 + kk) * b_sk) : 0.0;
+      const double b1 = (in && kg <= lim1) ? __ldcs(B1 + (int64_t)(k0 + kk) * b_sk) : 0.0;
+#pragma unroll
+      for (int m = 0; m < NMT; m++) {
+        const double a = a0[m * 8 * SK_F1D_KCP + kk];
+        dmma884(d[m][0][0], d[m][0][1], a, b0);
+        dmma884(d[m][1][0], d[m][1][1], a, b1);
+      }
+    }
+  }
+  if (!wactive) return;
+  const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG;
+#pragma unroll
+  for (int m = 0; m < NMT; m++) {
+    const int i = 8 * m + g;
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int j = jb + 8 * nt + 2 * t + h;
+        if (i < M && j < N) {
+          double* c = op.C + (int64_t)i * op.c_si + (int64_t)j * op.c_sj;
+          const double v = neg ? -d[m][nt][h] : d[m][nt][h];
+          *c = accum ? *c + v : v;
+        }
+      }
+  }
+}
+
 }  // namespace slmm
