@@ -455,6 +455,15 @@ struct PhaseBuilder {
     const bool small_tiles = !force_big && (!(op.M > 64 && op.N > 64) || (!lower && tb < 40 && op.K >= 128) ||
                                             (chain_small && lower && tb <= 64));
     const int64_t tiles = small_tiles ? ts : tb;
+    if (allow_split && !lower && (op.flags & GF_TRIL_B) && op.K >= 4096 && op.C != op.A && !small_tiles) {
+      // L11 * Z of a wide front: the tile of the last 128 columns would run the whole K = ns alone (one CTA, 2.7 ms at
+      // the 250K root).  K parts of 2048: a part's tiles left of its first column only write zeros, the others are
+      // equal pieces of work; the fixed-order reduction adds the parts.
+      const int kc = 2048;
+      const int S = (op.K + kc - 1) / kc;
+      split_k(op, S, kc, [&](GemmOp part) { part.flags = (ws_id ? GF_WS2 : GF_WS) | GF_TRIL_B; push(part, false); });
+      return;
+    }
     if (allow_split && !lower && !(op.flags & GF_TRIL_B) && tiles <= 148 && op.K >= 256 && op.C != op.A) {
       int S = (int)std::min<int64_t>(std::min<int64_t>(64, op.K / 64), std::max<int64_t>(1, 148 / tiles));   // one wave of CTAs
       const int kc = S > 0 ? (((op.K + S - 1) / S) + 15) / 16 * 16 : op.K;

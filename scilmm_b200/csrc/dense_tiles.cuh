@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(32 * (NWM * NWN + NPW), 1) gemm_tiles_kernel(c
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = op.M, N = op.N;
-  const int K = (flags & GF_TRIL_B) ? min(op.K, tn0 + TN) : op.K;   // triangular B: the rest of K multiplies zeros
+  // triangular B: the rest of K multiplies zeros; op.pad = first k of a split part (0 for whole ops)
+  const int K = (flags & GF_TRIL_B) ? min(op.K, max(0, tn0 + TN - op.pad)) : op.K;
   const int nslab = (K + KS - 1) / KS;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 32 * NPW); mbar_init(empty_bar + s, NCW); }
