@@ -265,6 +265,15 @@ struct Launch {
   int64_t aux_off = 0;
 };
 
+static bool skinny_dmma_on(int flavour) {       // SLMM_F1_DMMA=0 / SLMM_F2_DMMA=0: register-blocked streaming kernels only
+  static int on[3] = {-1, -1, -1};
+  if (on[flavour] < 0) {
+    const char* e = getenv(flavour == 1 ? "SLMM_F1_DMMA" : "SLMM_F2_DMMA");
+    on[flavour] = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on[flavour] == 1;
+}
+
 static bool tma_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("SLMM_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -423,12 +432,12 @@ struct PhaseBuilder {
     const int64_t target = f1 ? 148 * 8 : 148 * 4;
     const bool can_split = allow_split && op.C != op.A;
     if (can_split && nj < target) S = (int)std::min<int64_t>((target + nj - 1) / nj, std::max(1, op.K / kmin));
-    if (!f1) S = std::max(S, (op.K + SK_F2_KMAX - 1) / SK_F2_KMAX);      // F2 stages its whole K range of A
+    if (!f1 && skinny_mt < 8) S = std::max(S, (op.K + SK_F2_KMAX - 1) / SK_F2_KMAX);      // the register-blocked F2 stages its whole K range of A
     if (S > 1 && !can_split) return false;
     int kc = op.K;
     if (S > 1) {
       kc = (((op.K + S - 1) / S) + 15) / 16 * 16;
-      if (!f1) kc = std::min(kc, SK_F2_KMAX);
+      if (!f1 && skinny_mt < 8) kc = std::min(kc, SK_F2_KMAX);
       S = (op.K + kc - 1) / kc;
     }
     if (S <= 1) { GemmOp o = op; o.pad = 0; dst.push_back(o); }
@@ -662,8 +671,12 @@ static void init_kernel_attributes() {
   CUDA_OK(cudaFuncSetAttribute(gemm_tiles_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
   CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 12 * 8));
   CUDA_OK(cudaFuncSetAttribute(skinny_f2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_F2_KMAX * 16 * 8));
-  CUDA_OK(cudaFuncSetAttribute(skinny_f2_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SK_F2D_KP * 8));
-  CUDA_OK(cudaFuncSetAttribute(skinny_f2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SK_F2D_KP * 8));
+#define SKD_ATTR(NMT)                                                                                                         \
+  CUDA_OK(cudaFuncSetAttribute(skinny_f2_dmma_kernel<NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkDmma<NMT>::SMEM));   \
+  CUDA_OK(cudaFuncSetAttribute(skinny_f1_dmma_kernel<NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                               8 * NMT * ((NMT <= 4 ? 256 : 128) + 4) * (int)sizeof(double)));
+  SKD_ATTR(1) SKD_ATTR(2) SKD_ATTR(4) SKD_ATTR(8)
+#undef SKD_ATTR
   done = true;
 }
 
@@ -702,18 +715,19 @@ static void launch_one(slmm_chol* h, const Schedule& sch, const Launch& L, const
       const GemmOp* ops = sch.d_gemm + L.off;
       const int32_t* top = sch.d_tile_op + L.tile_off;
       const bool f1 = L.kind == Launch::SKINNY_F1;
-      static const bool f2_dmma = !(getenv("SLMM_F2_DMMA") && getenv("SLMM_F2_DMMA")[0] == '0');
-      static const bool f1_dmma = !(getenv("SLMM_F1_DMMA") && getenv("SLMM_F1_DMMA")[0] == '0');
-      if (f1 && f1_dmma && L.child_parity >= 8) {        // 5..16 right-hand sides: forward flavour on the tensor pipe
-        if (L.child_parity == 8) skinny_f1_dmma_kernel<1><<<L.grid, 256, 0, st>>>(ops, top);
-        else skinny_f1_dmma_kernel<2><<<L.grid, 256, 0, st>>>(ops, top);
+      const bool f2_dmma = skinny_dmma_on(2);
+      const bool f1_dmma = skinny_dmma_on(1);
+#define SKD_CASE(NMT)                                                                                                   \
+  if (f1) skinny_f1_dmma_kernel<NMT><<<L.grid, 256, 8 * NMT * ((NMT <= 4 ? 256 : 128) + 4) * sizeof(double), st>>>(ops, top); \
+  else skinny_f2_dmma_kernel<NMT><<<L.grid, 256, SkDmma<NMT>::SMEM, st>>>(ops, top);
+      if (L.child_parity >= 8 && (f1 ? f1_dmma : f2_dmma)) {   // 5..64 right-hand sides: streaming on the tensor pipe
+        if (L.child_parity == 8) { SKD_CASE(1) }
+        else if (L.child_parity <= 16) { SKD_CASE(2) }
+        else if (L.child_parity <= 32) { SKD_CASE(4) }
+        else { SKD_CASE(8) }
         break;
       }
-      if (!f1 && f2_dmma && L.child_parity >= 8) {       // 5..16 right-hand sides: backward flavour on the tensor pipe
-        if (L.child_parity == 8) skinny_f2_dmma_kernel<1><<<L.grid, 256, 8 * SK_F2D_KP * sizeof(double), st>>>(ops, top);
-        else skinny_f2_dmma_kernel<2><<<L.grid, 256, 16 * SK_F2D_KP * sizeof(double), st>>>(ops, top);
-        break;
-      }
+#undef SKD_CASE
 #define SK_CASE(MT)                                                                                          \
   if (f1) skinny_f1_kernel<MT><<<L.grid, SK_F1_COLS, 0, st>>>(ops, top);                                     \
   else skinny_f2_kernel<MT><<<L.grid, 256, SK_F2_KMAX * MT * sizeof(double), st>>>(ops, top);
@@ -1238,9 +1252,15 @@ static SolvePlan* get_plan(slmm_chol* h, int nrhs) {
   // consecutive diagonal blocks are serialised (same rows), and the late ones have far fewer tiles than SMs: without
   // split-K each still costs one full-K tile latency (170 us at the 250K config whatever its size)
   pb_rest.ws_id = 1;
-  if (nrhs <= 16 && skinny_enabled())    // narrow blocks: HBM-streaming kernels instead of DMMA tiles (skinny_ops.cuh)
-    pb.skinny_mt = nrhs <= 1 ? 1 : nrhs <= 2 ? 2 : nrhs <= 4 ? 4 : nrhs <= 8 ? 8 : nrhs <= 12 ? 12 : 16;
-  const bool lookahead = nrhs >= 64;     // narrow solves are launch-latency chains: nothing to overlap with
+  // narrow blocks: HBM-streaming kernels instead of DMMA tiles (skinny_ops.cuh).  Up to 16 columns always; up to
+  // SLMM_SKINNY_MAX (default 32: the local probe block at 4 GPUs) on the tensor-pipe streaming kernels.  Measured at
+  // the 250K config, solve / L*Z in ms, tiles -> streaming: 32 columns 7.7 -> 6.3 / 3.6 -> 2.2; 64 columns
+  // 8.2 -> 9.6 / 3.9 -> 3.7 (16 DMMA per streamed fragment: the tensor pipe, not HBM, bounds the stream there).
+  static const int skinny_max = !(skinny_dmma_on(1) && skinny_dmma_on(2)) ? 16 :
+      getenv("SLMM_SKINNY_MAX") ? std::max(16, std::min(64, atoi(getenv("SLMM_SKINNY_MAX")))) : 32;
+  if (nrhs <= skinny_max && skinny_enabled())
+    pb.skinny_mt = nrhs <= 1 ? 1 : nrhs <= 2 ? 2 : nrhs <= 4 ? 4 : nrhs <= 8 ? 8 : nrhs <= 12 ? 12 : nrhs <= 16 ? 16 : nrhs <= 32 ? 32 : 64;
+  const bool lookahead = nrhs >= 64 && pb.skinny_mt == 0;     // narrow solves are launch-latency chains: nothing to overlap with
   int last_bulk_ev = -1;
   // One phase: the chain's launches on the main stream; look-ahead remainders (if any) on the bulk stream, after
   // the diagonal step that produced their operand and before anything that touches the same rows again.

@@ -198,73 +198,86 @@ __global__ void __launch_bounds__(256, 2) skinny_f2_kernel(const GemmOp* __restr
 }
 
 // Backward-sweep flavour on the FP64 tensor pipe, for 5..16 right-hand sides.  Same tiling and operand staging as
-// skinny_f2_kernel (64 output columns per CTA, A(M x K <= 512) in shared memory), but the products run as DMMA
+// skinny_f2_kernel (64 output columns per CTA; A is staged in shared memory chunk by chunk along K, so K is not
+// limited), but the products run as DMMA
 // m8n8k4: a warp owns 8 output columns, its B fragment b[k = t][n = g] = B(j0 + g, kk + t) comes STRAIGHT from global
 // memory (each lane 8 bytes, a quad 32 contiguous bytes of one column of L: whole sectors, 256 bytes per warp load
 // like a coalesced load), the A fragments from shared memory (leading dimension = 4 mod 16: conflict free).  The
 // register-blocked kernel reads 12..16 shared-memory values per pair of streamed values and is bound by that; here it
-// is 2 per streamed value and the FMA work leaves the FP64 pipe.  NMT = row tiles of 8 (1: M <= 8, 2: M <= 16).
-constexpr int SK_F2D_KP = SK_F2_KMAX + 4;          // padded leading dimension of the staged operand
+// is 2 per streamed value and the FMA work leaves the FP64 pipe.  NMT = row tiles of 8 (M <= 8 NMT; 1, 2, 4, 8).
+template <int NMT> struct SkDmma {
+  // k chunk of the staged operand: the copy of A (8 NMT rows) must leave room for 2-3 resident CTAs per SM
+  static constexpr int KC = NMT <= 2 ? 512 : (NMT == 4 ? 256 : 128);
+  static constexpr int KP = KC + 4;                  // leading dimension = 4 mod 16: conflict-free fragment reads
+  static constexpr int SMEM = 8 * NMT * KP * (int)sizeof(double);
+  static constexpr int OCC = NMT <= 2 ? 3 : 2;
+};
 
 template <int NMT>
-__global__ void __launch_bounds__(256, 3) skinny_f2_dmma_kernel(const GemmOp* __restrict__ ops,
-                                                                const int32_t* __restrict__ tile_op) {
-  extern __shared__ double Ad[];                       // [8 * NMT][KP], zero beyond (M, K)
+__global__ void __launch_bounds__(256, SkDmma<NMT>::OCC) skinny_f2_dmma_kernel(const GemmOp* __restrict__ ops,
+                                                                              const int32_t* __restrict__ tile_op) {
+  constexpr int KC = SkDmma<NMT>::KC, KP = SkDmma<NMT>::KP;
+  extern __shared__ double Ad[];                       // [8 * NMT][KP], zero beyond (M, chunk)
   const int tile = blockIdx.x;
   const GemmOp& op = ops[tile_op[tile]];
   const int j0 = (tile - op.tile_start) * SK_F2_COLS;
   const int M = op.M, N = op.N, K = op.K, flags = op.flags;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int K4 = (K + 3) & ~3;
-  const int KP = ((K4 + 15) & ~15) + 4;
   const int32_t* __restrict__ kidx = op.a_kidx;
-  {
-    const int64_t a_sk = op.a_sk;
-    const int total = K * M;
-    for (int q0 = threadIdx.x; q0 < total; q0 += 4 * 256) {
-      double v[4];
-      int dst[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int q = q0 + u * 256;
-        const int k = q / M, i = q - k * M;
-        dst[u] = q < total ? i * KP + k : -1;
-        v[u] = q < total ? op.A[(int64_t)i + (int64_t)(kidx ? kidx[k] : k) * a_sk] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (dst[u] >= 0) Ad[dst[u]] = v[u];
-    }
-    // zero padding: rows M..8*NMT over [0, K4) and the k tail [K, K4) of the live rows
-    for (int q = threadIdx.x; q < (8 * NMT - M) * K4; q += 256) Ad[(M + q / K4) * KP + q % K4] = 0.0;
-    if (K4 > K)
-      for (int q = threadIdx.x; q < M * (K4 - K); q += 256) Ad[(q / (K4 - K)) * KP + K + q % (K4 - K)] = 0.0;
-  }
-  __syncthreads();
   const int jb = j0 + 8 * warp;                        // this warp's 8 output columns
-  if (jb >= N) return;
+  const bool wactive = jb < N;
   const int jg = min(jb + g, N - 1);                   // clamped: columns past N are computed and dropped
   const double* __restrict__ Bg = op.B + (int64_t)jg * op.b_sj + t;
   const double* a0 = Ad + g * KP + t;
   double d[NMT][2];
 #pragma unroll
   for (int m = 0; m < NMT; m++) d[m][0] = d[m][1] = 0.0;
-  int kk = 0;
-  for (; kk + 32 <= K; kk += 32) {                     // 8 independent 8-byte loads in flight per lane
-    double b[8];
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    const int kc = min(KC, K - k0), kc4 = (kc + 3) & ~3;
+    __syncthreads();
+    {
+      const int64_t a_sk = op.a_sk;
+      const int total = kc * M;
+      for (int q0 = threadIdx.x; q0 < total; q0 += 4 * 256) {
+        double v[4];
+        int dst[4];
 #pragma unroll
-    for (int u = 0; u < 8; u++) b[u] = __ldcs(Bg + kk + 4 * u);
+        for (int u = 0; u < 4; u++) {
+          const int q = q0 + u * 256;
+          const int k = q / M, i = q - k * M;
+          dst[u] = q < total ? i * KP + k : -1;
+          v[u] = q < total ? op.A[(int64_t)i + (int64_t)(kidx ? kidx[k0 + k] : k0 + k) * a_sk] : 0.0;
+        }
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+        for (int u = 0; u < 4; u++)
+          if (dst[u] >= 0) Ad[dst[u]] = v[u];
+      }
+      // zero padding: rows M..8*NMT over [0, kc4) and the k tail [kc, kc4) of the live rows
+      for (int q = threadIdx.x; q < (8 * NMT - M) * kc4; q += 256) Ad[(M + q / kc4) * KP + q % kc4] = 0.0;
+      if (kc4 > kc)
+        for (int q = threadIdx.x; q < M * (kc4 - kc); q += 256) Ad[(q / (kc4 - kc)) * KP + kc + q % (kc4 - kc)] = 0.0;
+    }
+    __syncthreads();
+    if (!wactive) continue;
+    const double* __restrict__ Bk = Bg + k0;
+    int kk = 0;
+    for (; kk + 32 <= kc; kk += 32) {                  // 8 independent 8-byte loads in flight per lane
+      double b[8];
 #pragma unroll
-      for (int m = 0; m < NMT; m++) dmma884(d[m][0], d[m][1], a0[m * 8 * KP + kk + 4 * u], b[u]);
+      for (int u = 0; u < 8; u++) b[u] = __ldcs(Bk + kk + 4 * u);
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int m = 0; m < NMT; m++) dmma884(d[m][0], d[m][1], a0[m * 8 * KP + kk + 4 * u], b[u]);
+    }
+    for (; kk < kc4; kk += 4) {
+      const double b = (kk + t < kc) ? __ldcs(Bk + kk) : 0.0;
+#pragma unroll
+      for (int m = 0; m < NMT; m++) dmma884(d[m][0], d[m][1], a0[m * 8 * KP + kk], b);
+    }
   }
-  for (; kk < K4; kk += 4) {
-    const double b = (kk + t < K) ? __ldcs(Bg + kk) : 0.0;
-#pragma unroll
-    for (int m = 0; m < NMT; m++) dmma884(d[m][0], d[m][1], a0[m * 8 * KP + kk], b);
-  }
+  if (!wactive) return;
   const bool accum = flags & GF_ACCUM, neg = flags & GF_NEG;
 #pragma unroll
   for (int m = 0; m < NMT; m++) {
@@ -284,14 +297,15 @@ __global__ void __launch_bounds__(256, 3) skinny_f2_dmma_kernel(const GemmOp* __
 // Forward flavour on the FP64 tensor pipe (5..16 right-hand sides): B(j, k) = B[j + k*b_sk], a warp owns 16 output
 // columns (two 8-column DMMA tiles); its B fragment b[k = t][n = g] = B(jb + g, kk + t) comes straight from global
 // memory - for a fixed k the 8 lanes of a g-group read 64 contiguous bytes, the 8 warps of a CTA 1 KB of that k-row.
-// A(M x K) is staged in K chunks of 256 as [i][260] (leading dimension = 4 mod 16: conflict-free fragment reads).
+// A(M x K) is staged in K chunks of 256 (128 for 64 rows) as [i][chunk + 4] (leading dimension = 4 mod 16:
+// conflict-free fragment reads).
 // Same op lists, tiling (128 columns per CTA) and split-K parts as skinny_f1_kernel.
-constexpr int SK_F1D_KCP = SK_F1_KC + 4;
 
 template <int NMT>
-__global__ void __launch_bounds__(256, 3) skinny_f1_dmma_kernel(const GemmOp* __restrict__ ops,
-                                                                const int32_t* __restrict__ tile_op) {
-  __shared__ double As[8 * NMT * SK_F1D_KCP];
+__global__ void __launch_bounds__(256, SkDmma<NMT>::OCC) skinny_f1_dmma_kernel(const GemmOp* __restrict__ ops,
+                                                                              const int32_t* __restrict__ tile_op) {
+  constexpr int SK_F1D_KC = NMT <= 4 ? 256 : 128, SK_F1D_KCP = SK_F1D_KC + 4;
+  extern __shared__ double As[];                       // [8 * NMT][SK_F1D_KCP]
   const int tile = blockIdx.x;
   const GemmOp& op = ops[tile_op[tile]];
   const int jt0 = (tile - op.tile_start) * SK_F1_COLS;
@@ -313,8 +327,8 @@ __global__ void __launch_bounds__(256, 3) skinny_f1_dmma_kernel(const GemmOp* __
 #pragma unroll
   for (int m = 0; m < NMT; m++) d[m][0][0] = d[m][0][1] = d[m][1][0] = d[m][1][1] = 0.0;
   const double* a0 = As + g * SK_F1D_KCP + t;
-  for (int k0 = 0; k0 < kend; k0 += SK_F1_KC) {
-    const int kc = min(SK_F1_KC, kend - k0), kc4 = (kc + 3) & ~3;
+  for (int k0 = 0; k0 < kend; k0 += SK_F1D_KC) {
+    const int kc = min(SK_F1D_KC, kend - k0), kc4 = (kc + 3) & ~3;
     __syncthreads();
     {
       const int total = kc * M;

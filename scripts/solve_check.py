@@ -17,7 +17,7 @@ ses = chol._session(mats, cov, y / y.std())
 ses.factor_at(sig)
 print("switches", {k: v for k, v in os.environ.items() if k.startswith("SLMM_")}, "logdet", ses.eng.logdet())
 torch.manual_seed(0)
-for k in (1, 2, 3, 4, 5, 8, 9, 12, 16, 17, 32, 128):
+for k in (1, 2, 3, 4, 5, 8, 9, 12, 16, 17, 24, 32, 48, 64, 128):
     B = torch.randn(n, k, dtype=torch.float64, device="cuda")
     X = ses.eng.solve_(B.clone())
     VX = sum(float(sig[j]) * ses.matset.spmm(j, X) for j in range(3))
@@ -27,3 +27,14 @@ for k in (1, 2, 3, 4, 5, 8, 9, 12, 16, 17, 32, 128):
     # forward half sweep of L Z returns Z with its rows permuted: compare permutation-invariant column moments
     rt = float(((Y * Y).sum(0) - (B * B).sum(0)).abs().max() / (B * B).sum(0).max()) + float((Y.sum(0) - B.sum(0)).abs().max()) / n
     print("nrhs %3d  residual %.3e  lmul->forward round trip %.3e" % (k, res, rt), flush=True)
+
+def tm(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+for k in (16, 32, 64, 128):
+    B = torch.randn(n, k, dtype=torch.float64, device="cuda")
+    print("nrhs %3d  solve %.2f ms  lmul %.2f ms" % (k, tm(lambda: ses.eng.solve_(B.clone())), tm(lambda: ses.eng.lmul(B))), flush=True)
