@@ -31,6 +31,7 @@ extern "C" {
 #define SLMM_ORDER_GIVEN 1
 #define SLMM_ORDER_METIS 2      /* nested dissection, the reference default ordering_method='nesdis' (:17) */
 #define SLMM_ORDER_MINDEG 3
+#define SLMM_ORDER_METIS_FAST 4 /* nested dissection, one separator per bisection: shorter analysis, ~2 % more flops */
 
 typedef struct slmm_chol slmm_chol_t;       /* symbolic analysis + numeric supernodal factor */
 typedef struct slmm_matset slmm_matset_t;   /* K device-resident CSR relationship matrices */

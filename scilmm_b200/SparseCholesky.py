@@ -98,6 +98,7 @@ class SparseCholesky(object):
 
     use_long / mode are accepted for signature compatibility (the engine is always supernodal LL' with
     32-bit row indices and 64-bit pointers).  ordering_method: 'nesdis' / 'metis' (nested dissection),
+    'nesdis_fast' (one separator per bisection: ~30 % shorter analysis, ~2 % more factorization flops),
     'natural', or pass `perm` (perm[new] = old) to force a permutation (parity mode: L is unique given P).
     rng: 'numpy' draws probe vectors from the global numpy stream exactly like the reference (:50);
          'device' draws them on the GPU (distribution-equivalent, not stream-identical);

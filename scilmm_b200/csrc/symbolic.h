@@ -13,7 +13,8 @@ namespace slmm {
 // boundary - the alignment bulk tensor copies (TMA) need for the global strides of a tensor map.
 inline int64_t panel_ld(int64_t nrow) { return (nrow + 1) & ~(int64_t)1; }
 
-enum Ordering { ORD_NATURAL = 0, ORD_GIVEN = 1, ORD_METIS = 2, ORD_MINDEG = 3 };
+enum Ordering { ORD_NATURAL = 0, ORD_GIVEN = 1, ORD_METIS = 2, ORD_MINDEG = 3,
+                ORD_METIS_FAST = 4 /* one separator per bisection instead of the best of three */ };
 
 struct SymbolicOptions {
   int ordering = ORD_METIS;

@@ -9,7 +9,8 @@ import scipy.sparse as sp
 from . import _lib
 from ._lib import check, lib, np_ptr
 
-ORDERINGS = {"natural": 0, "given": 1, "metis": 2, "nesdis": 2, "default": 2, "amd": 3, "mindeg": 3}
+ORDERINGS = {"natural": 0, "given": 1, "metis": 2, "nesdis": 2, "default": 2, "amd": 3, "mindeg": 3,
+             "nesdis_fast": 4, "metis_fast": 4}
 
 
 def _torch():

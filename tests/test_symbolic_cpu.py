@@ -259,3 +259,16 @@ def test_threaded_pattern_permutation_matches_the_sequential_one():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append([l for l in r.stdout.splitlines() if l.startswith(("HASH", "ASYM"))])
     assert outs[0] == outs[1] and outs[0][0].startswith("HASH") and outs[0][1] == "ASYM True", outs
+
+
+def test_fast_nested_dissection_is_a_valid_cheaper_ordering():
+    """ordering 'nesdis_fast' (one METIS separator per bisection instead of the best of three): a permutation, the
+    same analysis invariants, and a flop count within 15 % of the default on a pedigree pattern."""
+    import bench
+    from scilmm_b200 import engine as E
+    A, _, cov, y, info = bench.make_inputs(20000, 1e-3, 2)
+    a = E.SymbolicView(A, ordering="nesdis")
+    b = E.SymbolicView(A, ordering="nesdis_fast")
+    pb = b.arrays()["perm"]
+    assert np.array_equal(np.sort(pb), np.arange(A.shape[0]))
+    assert b.nnzL >= A.shape[0] and 0.85 < b.flops / a.flops < 1.15
