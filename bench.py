@@ -553,10 +553,12 @@ def main():
         st_q = ses_q.eng.stats()
         full_fit["nesdis_fast"] = {
             "wall_s": round(fit_q_s, 2), "setup_s": round(ses_q.setup_s, 2), "evaluations": int(ses_q.n_eval),
-            "factor_flops": st_q["flops"],
-            "sigma2_rel_diff_vs_default": float(np.max(np.abs(np.asarray(fit_q["covariance coefficients"]) -
-                                                              np.asarray(fit["covariance coefficients"])) /
-                                                       np.abs(np.asarray(fit["covariance coefficients"]))))}
+            "factor_flops": st_q["flops"], "sigma2": [float(v) for v in fit_q["covariance coefficients"]],
+            # another permutation gives another probe block (L Z)[P^-1] (reference :49-52): the two fits differ by
+            # Monte-Carlo noise of the trace estimate, measured here in units of the reported standard errors
+            "max_abs_diff_vs_default_over_se": float(np.max(np.abs(np.asarray(fit_q["covariance coefficients"]) -
+                                                                   np.asarray(fit["covariance coefficients"])) /
+                                                            np.asarray(fit["covariance std"])))}
         log("full fit, fast ordering", full_fit["nesdis_fast"])
         del ses_q, chol_q, fit_q, fit
         ses = None
