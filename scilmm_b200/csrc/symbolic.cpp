@@ -85,6 +85,8 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
       pos = c + 1;
     }
   }
+  const bool timing = getenv("SLMM_SYM_TIMING") != nullptr;
+  double tp = now_s(), t_graph = 0, t_metis = 0;
   // connected components by BFS
   std::vector<int32_t> comp(n, -1), queue(n);
   std::vector<int64_t> comp_start;
@@ -105,6 +107,7 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
     ncomp++;
   }
   comp_start.push_back(qt);
+  if (timing) { fprintf(stderr, "[ordering] %-28s %.3f s\n", "components (BFS)", now_s() - tp); tp = now_s(); }
   // order components by size (small first) so the big fronts end up last; stable within size
   std::vector<int> corder(ncomp);
   std::iota(corder.begin(), corder.end(), 0);
@@ -140,6 +143,7 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
       continue;
     }
     // METIS nested dissection on the component's graph (64-bit idx_t build shipped with the CUDA toolkit)
+    double tg = now_s();
     xadj.assign(m + 1, 0);
     int64_t cnt = 0;
     for (int k = 0; k < m; k++) {
@@ -170,11 +174,15 @@ void compute_ordering(int n, const int32_t* ap, const int32_t* ai, int method, s
     // worse one for the evaluation time itself or for repeated fits on one pattern.
     options[15] = fast_nd ? 1 : 3;    // METIS_OPTION_NSEPS
     for (const auto& kv : opt_metis) options[kv.first] = kv.second;
+    t_graph += now_s() - tg;
+    tg = now_s();
     int rc = METIS_NodeND(&nv, xadj.data(), adjncy.data(), nullptr, options, mperm.data(), miperm.data());
+    t_metis += now_s() - tg;
     if (rc != 1) throw std::runtime_error("METIS_NodeND failed");
     // METIS: A' = A(perm, perm); perm[new] = old
     for (int k = 0; k < m; k++) perm[out++] = queue[b + mperm[k]];
   }
+  if (timing) fprintf(stderr, "[ordering] graph build %.3f s, METIS_NodeND %.3f s, rest %.3f s\n", t_graph, t_metis, now_s() - tp - t_graph - t_metis);
   if (out != n) throw std::runtime_error("ordering lost vertices");
 }
 
